@@ -1,0 +1,53 @@
+"""The C oracle must reproduce what the UNMODIFIED reference planner code produced (tests/golden/*.npz, made by
+tests/golden/make_golden.py): this is what pins oracle/ to the reference for sampling, rollout loop, costs and
+softmin update. Tolerances: fp32, torch's reductions sum in a different order than the C loops."""
+import numpy as np
+import pytest
+
+import oracle_py as O
+from helpers import assert_close, case_cfg, golden_cases, load_golden, make_backend, tick
+from m3p2i_b200 import _abi as A
+
+RTOL, ATOL = 2e-4, 2e-4
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_oracle_reproduces_reference(name):
+    g = load_golden(name)
+    cfg = case_cfg(g)
+    o = make_backend(O.Oracle, cfg)
+    o.set_noise_table(g["delta"])
+    mm = bool(g["multi_modal"])
+    K, T, nu = int(g["K"]), int(g["T"]), int(g["nu"])
+    for i in range(int(g["calls"])):
+        action, cost_total, info = tick(o, g, i)
+        st = o.get_planner_state()
+        mean = np.asarray(st.mean_action[: T * nu], np.float32).reshape(T, nu)
+        assert_close(o.read_buffer(A.BUF_ACTIONS), g[f"actions_{i}"], RTOL, ATOL, f"{name}[{i}] actions")
+        assert_close(o.read_buffer(A.BUF_STATES), g[f"states_{i}"], RTOL, ATOL, f"{name}[{i}] states")
+        assert_close(cost_total, g[f"cost_total_{i}"], RTOL, ATOL, f"{name}[{i}] cost_total")
+        w = o.read_buffer(A.BUF_WEIGHTS)
+        assert_close(w[0], g[f"weights_{i}"], 2e-3, 1e-6, f"{name}[{i}] weights")
+        assert_close(mean, g[f"mean_action_{i}"], RTOL, ATOL, f"{name}[{i}] mean_action")
+        assert_close(action, g[f"action_{i}"], RTOL, ATOL, f"{name}[{i}] action")
+        if mm:
+            half = K // 2
+            assert_close(w[1, :half], g[f"weights_1_{i}"], 2e-3, 1e-6, f"{name}[{i}] weights_1")
+            assert_close(w[2, half:], g[f"weights_2_{i}"], 2e-3, 1e-6, f"{name}[{i}] weights_2")
+            for key in ("mean_action_1", "mean_action_2", "best_traj_1", "best_traj_2"):
+                got = np.asarray(getattr(st, key)[: T * nu], np.float32).reshape(T, nu)
+                assert_close(got, g[f"{key}_{i}"], RTOL, ATOL, f"{name}[{i}] {key}")
+            assert int(info.weight_pull > info.weight_push) == int(g[f"pull_preference_{i}"])
+        else:
+            got = np.asarray(st.best_traj[: T * nu], np.float32).reshape(T, nu)
+            assert_close(got, g[f"best_traj_{i}"], RTOL, ATOL, f"{name}[{i}] best_traj")
+            assert st.beta == pytest.approx(float(g[f"beta_{i}"]), rel=1e-12)
+        idx, tw, trajs = o.top_trajs(20)
+        assert_close(tw, g[f"top_values_{i}"], 2e-3, 1e-6, f"{name}[{i}] top_values")
+        # ties between equal weights may be ordered differently; compare the trajectories of matching indices
+        tv = g[f"top_values_{i}"]
+        distinct = np.array([tv[j] > 0 and (tv == tv[j]).sum() == 1 for j in range(20)])
+        assert distinct[0]
+        assert np.array_equal(idx[distinct], g[f"top_idx_{i}"][distinct]), f"{name}[{i}] top_idx"
+        assert_close(trajs[distinct], g[f"top_trajs_{i}"][distinct], RTOL, ATOL, f"{name}[{i}] top_trajs")
+    o.close()
