@@ -1,0 +1,148 @@
+// common.cuh — device-side parameter blocks and small math shared by the rollout / update / sim kernels.
+// Layout of everything in HBM is structure-of-arrays with the sample index fastest, so that a warp's
+// loads and stores of one field are one contiguous 128-byte line.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/m3p2i_b200.h"
+
+#define DEV __device__ __forceinline__
+
+namespace m3 {
+
+constexpr int kMaxNu = M3P2I_MAX_NU;
+constexpr int kMaxStatic = M3P2I_MAX_STATIC;
+constexpr int kMaxT = M3P2I_MAX_HORIZON;
+
+// number of floats of one environment in the persistent env buffer (field-major, [field][K])
+constexpr int kPointEnvFloats = 22;
+constexpr int kPandaEnvFloats = 53;
+
+// planner sequences kept on the device, each [T*nu]
+enum Seq { SEQ_MEAN = 0, SEQ_MEAN1, SEQ_MEAN2, SEQ_BEST, SEQ_BEST1, SEQ_BEST2, SEQ_COUNT };
+
+struct Static2 {       // planar oriented box (point_env walls / obstacle)
+  float cx, cy, hx, hy, c, s, mu, rad;
+};
+struct Static3 {       // 3-D oriented box (panda_env table / stands / plate)
+  float c[3], R[9], half[3], mu;
+};
+
+struct PointParams {
+  float robot_radius, robot_mass, robot_mu, drive_damping, drive_effort, gravity, ground_mu;
+  float contact_margin, baumgarte, slop, max_corr_vel;
+  float box_hx, box_hy, box_mass, box_inertia, box_mu, box_reff;
+  float dyn_hx, dyn_hy, dyn_mass, dyn_inertia, dyn_mu, dyn_reff;
+  int n_static;
+  Static2 st[kMaxStatic];
+};
+
+struct PandaParams {
+  float base[3], gravity;
+  float q_lower[9], q_upper[9], qd_limit[9], effort[9];
+  float drive_damping, arm_inertia, finger_mass, robot_mu;
+  float finger_half[3], finger_center[3], hand_half[3], hand_center[3];
+  float contact_margin, baumgarte, slop, max_corr_vel, penalty_stiffness;
+  float cube_half[2][3], cube_mass[2], cube_inertia[2], cube_mu[2];
+  int n_static, idx_table, idx_shelf;
+  Static3 st[kMaxStatic];
+};
+
+// per-command scalars (everything a rollout thread needs that is not per-sample)
+struct RolloutCfg {
+  int K, T, nu, Kg, offset;
+  int multi_modal, null_action, noise_mode, substeps, passes;
+  int task, gripper;
+  int env_live;     // 1: start from the persistent env buffer, 0: from the broadcast base state
+  int store_env;    // write the end state (and last velocity target) back to the env buffer
+  int open_loop;    // actions are supplied (m3p2i_rollout_actions) instead of sampled
+  float dt, gamma, u_scale, kp_suction, pre_height_diff, tilt_cos;
+  float u_min[kMaxNu], u_max[kMaxNu], sigma[kMaxNu];
+  float goal[8];
+  uint32_t seed_lo, seed_hi;
+};
+
+// values of sample 0 / sample K/2 of the global batch read by every sample's reach cost
+struct PandaRef {
+  float cube0[3];
+  int sel_axis;
+};
+
+struct RolloutBufs {
+  const float* noise;      // [T][nu][K] (table mode) or nullptr
+  const float* noise_row0; // [T][nu] noise of GLOBAL sample 0 for shards that do not own it, or nullptr
+  const float* seq;        // [SEQ_COUNT][T*nu] planner sequences (un-shifted; the kernel reads them shifted)
+  const float* actions_in; // [T][nu][K] open-loop actions or nullptr
+  const float* base;       // one env, field-major (broadcast start state)
+  float* env;              // [fields][K] persistent envs
+  float* vel_target;       // [nu][K]
+  float* actions;          // [T][nu][K]
+  float4* states;          // [T][K] (x, vx, y, vy) / (q1, qd1, q2, qd2)
+  float* cost_h;           // [T][K]
+  float* J;                // [K]  discounted cost
+  float* cost_sum;         // [K]  undiscounted sum
+  PandaRef* refs;          // [T]
+};
+
+// ------------------------------------------------------------------ small math
+DEV float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+DEV float signf(float v) { return v < 0.0f ? -1.0f : 1.0f; }
+
+struct V3 {
+  float x, y, z;
+};
+DEV V3 mk(float x, float y, float z) { V3 r = {x, y, z}; return r; }
+DEV V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+DEV V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+DEV V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+DEV V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+DEV V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+DEV float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+struct M33 {  // columns
+  V3 cx, cy, cz;
+};
+DEV V3 mul(const M33& R, V3 l) { return l.x * R.cx + l.y * R.cy + l.z * R.cz; }          // R l
+DEV V3 mulT(const M33& R, V3 o) { return mk(dot(R.cx, o), dot(R.cy, o), dot(R.cz, o)); }  // R^T o
+DEV V3 col(const M33& R, int i) { return i == 0 ? R.cx : (i == 1 ? R.cy : R.cz); }
+
+// rotation matrix of a unit quaternion (x,y,z,w)
+DEV M33 quat_to_R(float x, float y, float z, float w) {
+  M33 R;
+  R.cx = mk(1.0f - 2.0f * (y * y + z * z), 2.0f * (x * y + w * z), 2.0f * (x * z - w * y));
+  R.cy = mk(2.0f * (x * y - w * z), 1.0f - 2.0f * (x * x + z * z), 2.0f * (y * z + w * x));
+  R.cz = mk(2.0f * (x * z + w * y), 2.0f * (y * z - w * x), 1.0f - 2.0f * (x * x + y * y));
+  return R;
+}
+
+// ------------------------------------------------------------------ Philox4x32-10 counter RNG
+DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// four N(0,1) draws for counter (global sample, time step, dimension group); Box-Muller on 24-bit uniforms
+DEV void normal4(uint32_t seed_lo, uint32_t seed_hi, uint32_t kg, uint32_t t, uint32_t g, float z[4]) {
+  uint32_t r[4];
+  philox4x32_10(kg, t, g, 0u, seed_lo, seed_hi, r);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float u1 = ((float)(r[2 * i] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float u2 = ((float)(r[2 * i + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    z[2 * i] = rad * cs;
+    z[2 * i + 1] = rad * sn;
+  }
+}
+
+}  // namespace m3

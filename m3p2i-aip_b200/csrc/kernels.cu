@@ -1,0 +1,508 @@
+// kernels.cu — the MPPI hot path on sm_100a: fused sample -> rollout -> cost kernel, softmin statistics,
+// weighted action sums, mean update. One thread owns one sample trajectory; all HBM traffic is sample-fastest SoA.
+#include "kernels.cuh"
+#include "panda_env.cuh"
+#include "point_env.cuh"
+
+namespace m3 {
+
+constexpr int kRolloutBlock = 32;   // one warp per CTA: at K = 4096 the 128 CTAs land on 128 different SMs
+constexpr int kStatsBlock = 1024;
+constexpr int kSumBlock = 256;
+
+template <int ENV> struct EnvOf;
+template <> struct EnvOf<M3P2I_ENV_POINT> { using Env = PointEnv; using Params = PointParams; static constexpr int NU = 2; };
+template <> struct EnvOf<M3P2I_ENV_PANDA> { using Env = PandaEnv; using Params = PandaParams; static constexpr int NU = 9; };
+
+DEV void env_step(PointEnv& e, const PointParams& P, const float* u, const RolloutCfg& c) {
+  point_step(e, P, u, c.dt, c.substeps, c.passes);
+}
+DEV void env_step(PandaEnv& e, const PandaParams& P, const float* u, const RolloutCfg& c) {
+  panda_step(e, P, u, c.dt, c.substeps, c.passes);
+}
+DEV float env_cost(PointEnv& e, const PointParams&, const RolloutCfg& c, int kg, const PandaRef*) {
+  return point_cost(e, c, kg);
+}
+DEV float env_cost(PandaEnv& e, const PandaParams& P, const RolloutCfg& c, int kg, const PandaRef* ref) {
+  PandaRef r;
+  if (ref) r = *ref;
+  else { r.cube0[0] = e.cube[0].p.x; r.cube0[1] = e.cube[0].p.y; r.cube0[2] = e.cube[0].p.z; r.sel_axis = sel_axis_of(e.cube[0]); }
+  return panda_cost(e, P, c, kg, r);
+}
+
+// Perturbed action of GLOBAL sample kg at step t (mppi.py:392-416). `kl` is its row in this shard's tables, or -1.
+// The planner sequences are read time-shifted by one step (MPPI._shift_action, mppi.py:266-273): the shift itself
+// is applied to the stored mean in k_finish.
+template <int NU>
+DEV void sample_action(const RolloutCfg& c, const RolloutBufs& b, int kg, int kl, int t, float* u) {
+  const int K = c.K, TN = c.T * NU, half = c.Kg / 2;
+  if (c.open_loop) {
+#pragma unroll
+    for (int d = 0; d < NU; ++d) u[d] = c.u_scale * b.actions_in[(size_t)(t * NU + d) * K + kl];
+  } else {
+    const int ts = min(t + 1, c.T - 1);
+    const float* mean = b.seq + (c.multi_modal ? (kg < half ? SEQ_MEAN1 : SEQ_MEAN2) : SEQ_MEAN) * TN + ts * NU;
+    float z[4];
+#pragma unroll
+    for (int d = 0; d < NU; ++d) {
+      float delta;
+      if (c.noise_mode == M3P2I_NOISE_PHILOX) {
+        if ((d & 3) == 0) normal4(c.seed_lo, c.seed_hi, (uint32_t)kg, (uint32_t)t, (uint32_t)(d >> 2), z);
+        delta = z[d & 3];
+      } else if (kl >= 0) {
+        delta = b.noise ? b.noise[(size_t)(t * NU + d) * K + kl] : 0.0f;
+      } else {
+        delta = b.noise_row0 ? b.noise_row0[t * NU + d] : 0.0f;
+      }
+      if (kg == c.Kg - 1) delta = 0.0f;  // delta[-1] = 0: the mean itself is always a sample (mppi.py:392)
+      float v = mean[d] + delta * c.sigma[d];
+      v = fmaxf(fminf(v, c.u_max[d]), c.u_min[d]);
+      if (c.multi_modal) {
+        if (kg == 0) v = b.seq[SEQ_BEST1 * TN + ts * NU + d];
+        if (kg == half) v = b.seq[SEQ_BEST2 * TN + ts * NU + d];
+      }
+      if (NU == 9 && d >= 7) {
+        if (c.gripper == M3P2I_GRIPPER_OPEN) v = 1.5f;
+        else if (c.gripper == M3P2I_GRIPPER_CLOSE) v = -1.5f;
+      }
+      u[d] = c.u_scale * v;
+    }
+  }
+  if (c.null_action && kg == c.Kg - 1) {
+#pragma unroll
+    for (int d = 0; d < NU; ++d) u[d] = 0.0f;
+  }
+}
+
+// ------------------------------------------------------------------ fused rollout
+// noise -> perturbation -> clamp -> T x (dynamics step, task cost, discounted accumulate) with per-step stores of
+// the action planes, the float4 state row and the cost (mppi.py:275-332 with reactive_tamp.py:63-73 inlined).
+template <int ENV>
+__global__ void __launch_bounds__(kRolloutBlock)
+k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename EnvOf<ENV>::Params P, const RolloutBufs b) {
+  using Env = typename EnvOf<ENV>::Env;
+  constexpr int NU = EnvOf<ENV>::NU;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= c.K) return;
+  const int K = c.K, kg = c.offset + k;
+  Env e;
+  if (c.env_live) e.load(b.env, K, k);
+  else e.load(b.base, 1, 0);
+  float run = 0.0f, J = 0.0f, g = 1.0f;
+  float u[NU];
+  for (int t = 0; t < c.T; ++t) {
+    sample_action<NU>(c, b, kg, k, t, u);
+    env_step(e, P, u, c);
+    const float cost = env_cost(e, P, c, kg, (ENV == M3P2I_ENV_PANDA && b.refs) ? &b.refs[t] : nullptr);
+    run += cost;
+    J += g * cost;
+    g *= c.gamma;
+#pragma unroll
+    for (int d = 0; d < NU; ++d) b.actions[(size_t)(t * NU + d) * K + k] = u[d];
+    b.states[(size_t)t * K + k] = e.state_row();
+    b.cost_h[(size_t)t * K + k] = cost;
+  }
+  b.J[k] = J;
+  b.cost_sum[k] = run;
+  if (c.store_env) {
+    e.store(b.env, K, k);
+#pragma unroll
+    for (int d = 0; d < NU; ++d) b.vel_target[(size_t)d * K + k] = u[d];
+  }
+}
+
+// Rows 0 and Kg/2 of the GLOBAL batch, replayed by two threads so that every sample's reach cost can read the cube
+// position of sample 0 (cost_functions.py:98,102-103) and the cube axis picked from the first row of the second
+// half (skill_utils.py:275-279 on [half_samples:], cost_functions.py:151-152).
+__global__ void k_refs(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
+  const int which = threadIdx.x;
+  if (which > (c.multi_modal ? 1 : 0)) return;
+  const int kg = which == 0 ? 0 : c.Kg / 2;
+  const int kl = (kg >= c.offset && kg < c.offset + c.K) ? kg - c.offset : -1;
+  PandaEnv e;
+  if (c.env_live && kl >= 0) e.load(b.env, c.K, kl);
+  else e.load(b.base, 1, 0);
+  float u[9];
+  for (int t = 0; t < c.T; ++t) {
+    sample_action<9>(c, b, kg, kl, t, u);
+    panda_step(e, P, u, c.dt, c.substeps, c.passes);
+    if (which == 0) {
+      b.refs[t].cube0[0] = e.cube[0].p.x; b.refs[t].cube0[1] = e.cube[0].p.y; b.refs[t].cube0[2] = e.cube[0].p.z;
+      if (!c.multi_modal) b.refs[t].sel_axis = sel_axis_of(e.cube[0]);
+    } else {
+      b.refs[t].sel_axis = sel_axis_of(e.cube[0]);
+    }
+  }
+}
+
+void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp,
+                    const RolloutBufs& b, bool need_refs, cudaStream_t st, int* launches) {
+  const int grid = (c.K + kRolloutBlock - 1) / kRolloutBlock;
+  if (env_type == M3P2I_ENV_POINT) {
+    k_rollout<M3P2I_ENV_POINT><<<grid, kRolloutBlock, 0, st>>>(c, *pp, b);
+    ++*launches;
+  } else {
+    if (need_refs) {
+      k_refs<<<1, 32, 0, st>>>(c, *qp, b);
+      ++*launches;
+    }
+    k_rollout<M3P2I_ENV_PANDA><<<grid, kRolloutBlock, 0, st>>>(c, *qp, b);
+    ++*launches;
+  }
+}
+
+// ------------------------------------------------------------------ block reductions (fixed order => reproducible)
+DEV float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int BLOCK>
+DEV float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  float r = (threadIdx.x < BLOCK / 32) ? sh[threadIdx.x] : 0.0f;
+  if (wid == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) sh[0] = r;
+  __syncthreads();
+  r = sh[0];
+  return r;
+}
+// minimum and the FIRST index attaining it
+template <int BLOCK>
+DEV void block_argmin(float v, int i, float* shv, int* shi, float& vmin, int& imin) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+  __syncthreads();
+  if (lane == 0) { shv[wid] = v; shi[wid] = i; }
+  __syncthreads();
+  if (wid == 0) {
+    v = (threadIdx.x < BLOCK / 32) ? shv[threadIdx.x] : INFINITY;
+    i = (threadIdx.x < BLOCK / 32) ? shi[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+      if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+    if (threadIdx.x == 0) { shv[0] = v; shi[0] = i; }
+  }
+  __syncthreads();
+  vmin = shv[0]; imin = shi[0];
+}
+
+// ------------------------------------------------------------------ softmin statistics
+// _exp_util (mppi.py:430-456) / _multi_modal_exp_util + update_infinite_beta (m3p2i.py:24-64): min-shift, exp,
+// normaliser eta, on-the-fly beta search, weights. One CTA; the beta search loops on the device (no host sync).
+__global__ void __launch_bounds__(kStatsBlock) k_stats(const UpdateCfg u, const UpdateBufs b) {
+  __shared__ float shv[32];
+  __shared__ int shi[32];
+  const int Kg = u.Kg, half = Kg / 2;
+  const float* J = b.J_global;
+  Stats* S = b.stats;
+  const int nsets = u.multi_modal ? 3 : 1;
+  int iters = 0;
+  for (int i = threadIdx.x; i < 3 * Kg; i += kStatsBlock) b.weights[i] = 0.0f;
+  __syncthreads();
+  for (int s = 0; s < nsets; ++s) {
+    const int lo = s == 2 ? half : 0, n = s == 0 ? Kg : (s == 1 ? half : Kg - half);
+    float v = INFINITY;
+    int vi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += kStatsBlock) {
+      const float x = J[lo + i];
+      if (x < v) { v = x; vi = i; }
+    }
+    float jmin; int imin;
+    block_argmin<kStatsBlock>(v, vi, shv, shi, jmin, imin);
+    if (imin == 0x7fffffff) { imin = 0; jmin = J[lo]; }  // all-NaN / all-inf costs
+    double beta = u.multi_modal ? 1.0 : S->beta;  // multi-modal: the search restarts from 1 every call (m3p2i.py:58-60)
+    float scale, eta;
+    for (;;) {
+      scale = (float)(-1.0 / beta);
+      float acc = 0.0f;
+      for (int i = threadIdx.x; i < n; i += kStatsBlock) acc += expf(scale * (J[lo + i] - jmin));
+      eta = block_sum<kStatsBlock>(acc, shv);
+      if (!u.multi_modal) break;
+      ++iters;
+      if (eta > 10.0f) beta = beta * 0.9;
+      else if (eta < 3.0f) beta = beta * 1.2;
+      else break;  // also taken when eta is NaN (more than 10 samples tie at the minimum), as in the reference
+      if (iters > 100000) break;
+    }
+    const float inv = 1.0f / eta;
+    for (int i = threadIdx.x; i < n; i += kStatsBlock)
+      b.weights[(size_t)s * Kg + lo + i] = inv * expf(scale * (J[lo + i] - jmin));
+    if (threadIdx.x == 0) {
+      S->scale[s] = scale; S->inv_eta[s] = inv; S->eta[s] = eta; S->beta_used[s] = (float)beta; S->jmin[s] = jmin;
+      S->best_idx[s] = lo + imin;
+    }
+    __syncthreads();
+  }
+  if (u.multi_modal) {  // get_pull_preference (m3p2i.py:16-22)
+    float a = 0.0f, c = 0.0f;
+    for (int i = threadIdx.x; i < half; i += kStatsBlock) a += b.weights[i];
+    for (int i = half + threadIdx.x; i < Kg; i += kStatsBlock) c += b.weights[i];
+    a = block_sum<kStatsBlock>(a, shv);
+    c = block_sum<kStatsBlock>(c, shv);
+    if (threadIdx.x == 0) { S->weight_push = a; S->weight_pull = c; }
+  }
+  if (threadIdx.x == 0) {
+    S->beta_iters = iters;
+    if (!u.multi_modal) {
+      S->weight_push = 0.0f; S->weight_pull = 0.0f;
+      if (u.env_type == M3P2I_ENV_PANDA) {  // beta adapts across calls (mppi.py:446-454)
+        if (S->eta[0] > 20.0f) S->beta = S->beta * 0.9;
+        else if (S->eta[0] < 10.0f) S->beta = S->beta * 1.2;
+      }
+    }
+  }
+}
+
+void launch_stats(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches) {
+  k_stats<<<1, kStatsBlock, 0, st>>>(u, b);
+  ++*launches;
+}
+
+// ------------------------------------------------------------------ weighted action sums
+// CTA j < T*nu reduces plane j of the action buffer over this shard's K samples with the three weight sets
+// (mppi.py:498-499, m3p2i.py:80-86) and gathers the best rows (mppi.py:494-496, m3p2i.py:75-78);
+// CTA T*nu sums the undiscounted costs (the mean term of mppi.py:325).
+__global__ void __launch_bounds__(kSumBlock) k_wsum(const UpdateCfg u, const UpdateBufs b) {
+  __shared__ float sh[32];
+  const int K = u.K, Kg = u.Kg, half = Kg / 2, TN = u.T * u.nu, j = blockIdx.x;
+  if (j == TN) {
+    float a = 0.0f;
+    for (int k = threadIdx.x; k < K; k += kSumBlock) a += b.cost_sum[k];
+    a = block_sum<kSumBlock>(a, sh);
+    if (threadIdx.x == 0) b.partials[6 * TN] = a;
+    return;
+  }
+  const float* plane = b.actions + (size_t)j * K;
+  const float* w0 = b.weights + u.offset;
+  const float* w1 = b.weights + (size_t)Kg + u.offset;
+  const float* w2 = b.weights + 2 * (size_t)Kg + u.offset;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+  for (int k = threadIdx.x; k < K; k += kSumBlock) {
+    const float a = plane[k];
+    s0 += w0[k] * a;
+    if (u.multi_modal) {
+      if (u.offset + k < half) s1 += w1[k] * a;
+      else s2 += w2[k] * a;
+    }
+  }
+  s0 = block_sum<kSumBlock>(s0, sh);
+  if (u.multi_modal) { s1 = block_sum<kSumBlock>(s1, sh); s2 = block_sum<kSumBlock>(s2, sh); }
+  if (threadIdx.x == 0) {
+    b.partials[j] = s0; b.partials[TN + j] = s1; b.partials[2 * TN + j] = s2;
+    const int nsets = u.multi_modal ? 3 : 1;
+    for (int s = 0; s < 3; ++s) {
+      float row = 0.0f;
+      if (s < nsets) {
+        const int bl = b.stats->best_idx[s] - u.offset;
+        if (bl >= 0 && bl < K) row = plane[bl];
+      }
+      b.partials[(3 + s) * TN + j] = row;
+    }
+  }
+}
+
+void launch_wsum(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches) {
+  k_wsum<<<u.T * u.nu + 1, kSumBlock, 0, st>>>(u, b);
+  ++*launches;
+}
+
+// ------------------------------------------------------------------ mean update, filter, cost_total
+// mppi.py:494-503 / m3p2i.py:75-87 on the (all-reduced) partial sums; the one-step shift of the stored mean
+// (mppi.py:237,266-273) is folded in; Savitzky-Golay as a [T,T] matrix (mppi.py:257-263); cost_total aliasing
+// quirk cost_total = sum_t c + mean_k(sum_t c) (mppi.py:282-284,325).
+__global__ void __launch_bounds__(kSumBlock) k_finish(const UpdateCfg u, const UpdateBufs b) {
+  extern __shared__ float smean[];  // [T*nu] new mean
+  const int T = u.T, nu = u.nu, TN = T * nu;
+  const float a2 = u.step_size_mean, a1 = (float)(1.0 - (double)u.step_size_mean);
+  const float* part = b.partials;
+  float* seq = b.seq;
+  for (int i = threadIdx.x; i < TN; i += kSumBlock) {
+    const int t = i / nu, d = i - t * nu;
+    const int ts = u.shift ? min(t + 1, T - 1) : t;
+    smean[i] = a1 * seq[SEQ_MEAN * TN + ts * nu + d] + a2 * part[i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TN; i += kSumBlock) {
+    seq[SEQ_MEAN * TN + i] = smean[i];
+    if (u.multi_modal) {
+      seq[SEQ_MEAN1 * TN + i] = part[TN + i];
+      seq[SEQ_MEAN2 * TN + i] = part[2 * TN + i];
+      seq[SEQ_BEST1 * TN + i] = part[4 * TN + i];
+      seq[SEQ_BEST2 * TN + i] = part[5 * TN + i];
+    } else {
+      seq[SEQ_BEST * TN + i] = part[3 * TN + i];
+    }
+    float out = smean[i];
+    if (u.filter_u && b.filt) {
+      const int t = i / nu, d = i - t * nu;
+      float acc = 0.0f;
+      for (int jj = 0; jj < T; ++jj) acc += b.filt[t * T + jj] * smean[jj * nu + d];
+      out = acc;
+    }
+    b.result[i] = out;
+    b.result[TN + i] = smean[i];
+  }
+  const float mean_cost = part[6 * TN] / (float)u.Kg;
+  for (int k = threadIdx.x; k < u.K; k += kSumBlock) b.cost_total[k] = b.cost_sum[k] + mean_cost;
+  if (threadIdx.x == 0) {
+    const Stats* S = b.stats;
+    M3P2ICommandInfo* in = b.info;
+    for (int s = 0; s < 3; ++s) {
+      const bool on = s == 0 || u.multi_modal;
+      in->eta[s] = on ? S->eta[s] : 0.0f; in->beta[s] = on ? S->beta_used[s] : 0.0f;
+      in->min_cost[s] = on ? S->jmin[s] : 0.0f; in->best_idx[s] = on ? S->best_idx[s] : 0;
+    }
+    in->weight_push = S->weight_push; in->weight_pull = S->weight_pull;
+    in->mean_cost_sum = mean_cost;
+    in->beta_iters = S->beta_iters;
+  }
+}
+
+void launch_finish(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches) {
+  k_finish<<<1, kSumBlock, sizeof(float) * u.T * u.nu, st>>>(u, b);
+  ++*launches;
+}
+
+__global__ void k_discount(const float* cost_h, float* J, float* cost_sum, int K, int T, float gamma) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float run = 0.0f, acc = 0.0f, g = 1.0f;
+  for (int t = 0; t < T; ++t) {
+    const float c = cost_h[(size_t)t * K + k];
+    run += c; acc += g * c; g *= gamma;
+  }
+  J[k] = acc; cost_sum[k] = run;
+}
+
+void launch_discount(const float* cost_h, float* J, float* cost_sum, int K, int T, float gamma, cudaStream_t st,
+                     int* launches) {
+  k_discount<<<(K + 127) / 128, 128, 0, st>>>(cost_h, J, cost_sum, K, T, gamma);
+  ++*launches;
+}
+
+// ------------------------------------------------------------------ persistent K-env sim facade
+__global__ void k_sim_reset(const float* base, float* env, int K, int nf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  for (int f = 0; f < nf; ++f) env[(size_t)f * K + k] = base[f];
+}
+
+void launch_sim_reset(int env_type, const float* base, float* env, int K, cudaStream_t st) {
+  const int nf = env_type == M3P2I_ENV_POINT ? kPointEnvFloats : kPandaEnvFloats;
+  k_sim_reset<<<(K + 127) / 128, 128, 0, st>>>(base, env, K, nf);
+}
+
+template <int ENV>
+__global__ void __launch_bounds__(kRolloutBlock)
+k_sim_step(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename EnvOf<ENV>::Params P, float* env,
+           const float* vel_target) {
+  constexpr int NU = EnvOf<ENV>::NU;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= c.K) return;
+  typename EnvOf<ENV>::Env e;
+  e.load(env, c.K, k);
+  float u[NU];
+#pragma unroll
+  for (int d = 0; d < NU; ++d) u[d] = vel_target[(size_t)d * c.K + k];
+  env_step(e, P, u, c);
+  e.store(env, c.K, k);
+}
+
+void launch_sim_step(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp, float* env,
+                     const float* vel_target, cudaStream_t st) {
+  const int grid = (c.K + kRolloutBlock - 1) / kRolloutBlock;
+  if (env_type == M3P2I_ENV_POINT) k_sim_step<M3P2I_ENV_POINT><<<grid, kRolloutBlock, 0, st>>>(c, *pp, env, vel_target);
+  else k_sim_step<M3P2I_ENV_PANDA><<<grid, kRolloutBlock, 0, st>>>(c, *qp, env, vel_target);
+}
+
+// Objective.compute_cost on the persistent envs; reach costs read rows 0 and K/2 of the batch directly
+template <int ENV>
+__global__ void __launch_bounds__(kRolloutBlock)
+k_sim_cost(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename EnvOf<ENV>::Params P, float* env,
+           float* out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= c.K) return;
+  typename EnvOf<ENV>::Env e;
+  e.load(env, c.K, k);
+  PandaRef ref;
+  const PandaRef* rp = nullptr;
+  if (ENV == M3P2I_ENV_PANDA && c.task == M3P2I_TASK_REACH) {
+    PandaEnv r0;
+    r0.load(env, c.K, 0);
+    ref.cube0[0] = r0.cube[0].p.x; ref.cube0[1] = r0.cube[0].p.y; ref.cube0[2] = r0.cube[0].p.z;
+    if (c.multi_modal) r0.load(env, c.K, c.Kg / 2);
+    ref.sel_axis = sel_axis_of(r0.cube[0]);
+    rp = &ref;
+  }
+  out[k] = env_cost(e, P, c, c.offset + k, rp);
+  e.store(env, c.K, k);  // the pull cost arms the suction forces
+}
+
+void launch_sim_cost(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp, float* env,
+                     float* out_cost, cudaStream_t st) {
+  const int grid = (c.K + kRolloutBlock - 1) / kRolloutBlock;
+  if (env_type == M3P2I_ENV_POINT) k_sim_cost<M3P2I_ENV_POINT><<<grid, kRolloutBlock, 0, st>>>(c, *pp, env, out_cost);
+  else k_sim_cost<M3P2I_ENV_PANDA><<<grid, kRolloutBlock, 0, st>>>(c, *qp, env, out_cost);
+}
+
+__global__ void k_sim_links(const __grid_constant__ PandaParams P, const float* env, float* links, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  PandaEnv e;
+  e.load(env, K, k);
+  float out[39];
+  panda_links(P, e.q, e.qd, out);
+  for (int i = 0; i < 39; ++i) links[(size_t)k * 39 + i] = out[i];
+}
+
+void launch_sim_links(const PandaParams* qp, const float* env, float* links, int K, cudaStream_t st) {
+  k_sim_links<<<(K + 63) / 64, 64, 0, st>>>(*qp, env, links, K);
+}
+
+__global__ void k_noise_dump(const __grid_constant__ RolloutCfg c, float* out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= c.K) return;
+  const int kg = c.offset + k;
+  for (int t = 0; t < c.T; ++t) {
+    float z[4];
+    for (int d = 0; d < c.nu; ++d) {
+      if ((d & 3) == 0) normal4(c.seed_lo, c.seed_hi, (uint32_t)kg, (uint32_t)t, (uint32_t)(d >> 2), z);
+      out[(size_t)(t * c.nu + d) * c.K + k] = z[d & 3];
+    }
+  }
+}
+
+void launch_noise_dump(const RolloutCfg& c, float* out, cudaStream_t st) {
+  k_noise_dump<<<(c.K + 127) / 128, 128, 0, st>>>(c, out);
+}
+
+__global__ void k_transpose(const float* in, float* out, int rows, int cols) {
+  __shared__ float tile[32][33];
+  int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 32 + threadIdx.y;
+  for (int j = 0; j < 32; j += 8)
+    if (x < cols && y + j < rows) tile[threadIdx.y + j][threadIdx.x] = in[(size_t)(y + j) * cols + x];
+  __syncthreads();
+  x = blockIdx.y * 32 + threadIdx.x; y = blockIdx.x * 32 + threadIdx.y;
+  for (int j = 0; j < 32; j += 8)
+    if (x < rows && y + j < cols) out[(size_t)(y + j) * rows + x] = tile[threadIdx.x][threadIdx.y + j];
+}
+
+void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  k_transpose<<<grid, block, 0, st>>>(in, out, rows, cols);
+}
+
+}  // namespace m3

@@ -1,0 +1,58 @@
+// kernels.cuh — launch interface between the C ABI (api.cu) and the device code (kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace m3 {
+
+struct UpdateCfg {
+  int K, T, nu, Kg, offset, multi_modal, env_type, filter_u, shift;
+  float gamma, step_size_mean;
+};
+
+// device-resident planner scalars and the statistics of the last softmin (written by k_stats)
+struct Stats {
+  double beta;          // single-mode inverse temperature carried across commands (mppi.py:184,446-454)
+  float scale[3];       // (float)(-1/beta) used for each weight set (all, first half, second half)
+  float inv_eta[3];
+  float eta[3];
+  float beta_used[3];
+  float jmin[3];
+  int best_idx[3];      // global index of the best sample of each set
+  float weight_push, weight_pull;
+  int beta_iters;
+};
+
+struct UpdateBufs {
+  const float* J_global;   // [Kg]
+  float* weights;          // [3][Kg]
+  Stats* stats;
+  const float* actions;    // [T][nu][K]
+  const float* cost_sum;   // [K]
+  float* partials;         // [6*T*nu + 1]
+  float* seq;              // [SEQ_COUNT][T*nu]
+  const float* filt;       // [T][T] or nullptr
+  float* cost_total;       // [K]
+  float* result;           // [T*nu] filtered action, followed by [T*nu] unfiltered mean
+  M3P2ICommandInfo* info;  // device copy
+};
+
+void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp,
+                    const RolloutBufs& b, bool need_refs, cudaStream_t st, int* launches);
+void launch_stats(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches);
+void launch_wsum(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches);
+void launch_finish(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches);
+// J[k] = sum_t gamma^t cost_h[t][k], cost_sum[k] = sum_t cost_h[t][k] for caller-supplied cost_h (update_only)
+void launch_discount(const float* cost_h, float* J, float* cost_sum, int K, int T, float gamma, cudaStream_t st,
+                     int* launches);
+
+void launch_sim_reset(int env_type, const float* base, float* env, int K, cudaStream_t st);
+void launch_sim_step(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp, float* env,
+                     const float* vel_target, cudaStream_t st);
+void launch_sim_cost(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp, float* env,
+                     float* out_cost, cudaStream_t st);
+void launch_sim_links(const PandaParams* qp, const float* env, float* links /*[K][39]*/, int K, cudaStream_t st);
+void launch_noise_dump(const RolloutCfg& c, float* out /*[T][nu][K]*/, cudaStream_t st);
+// [rows][cols] -> [cols][rows]
+void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st);
+
+}  // namespace m3

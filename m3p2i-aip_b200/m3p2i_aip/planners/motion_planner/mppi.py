@@ -1,0 +1,293 @@
+"""MPPI controller with the reference's API, running on the native B200 hot path.
+
+Mirrors planners/motion_planner/mppi.py: MPPIConfig (:9-59), MPPI.__init__ (:82-203), command (:211-264) and the
+attributes a caller reads afterwards (weights, cost_total, states, actions, mean_action, best_traj*, top_trajs,
+delta). Two execution paths:
+
+* fused (default when `dynamics` / `running_cost` are bound methods of an object whose `.sim` is this package's
+  IsaacGymWrapper and `.objective` this package's Objective -- exactly what scripts/reactive_tamp.py:37-41,63-73
+  passes): one m3p2i_command() call = noise, perturbation, T-step rollout, costs, softmin, mean update on the GPU.
+  The Python callbacks are not invoked.
+* generic (any other callables): the reference's T-step Python loop (mppi.py:296-315) calls the user's dynamics
+  and running_cost; perturbation and the softmin / weighted update (mppi.py:381-416, 430-456, 485-518) go through
+  m3p2i_update_only().
+"""
+from dataclasses import dataclass
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+
+from m3p2i_b200 import _abi as A
+from m3p2i_b200 import native
+from m3p2i_b200 import scene as S
+from m3p2i_aip.utils import mppi_utils
+
+
+@dataclass
+class MPPIConfig(object):
+    num_samples: int = 200
+    horizon: int = 12
+    nx: int = 4
+    mppi_mode: str = 'halton-spline'
+    sampling_method: str = "halton"   # "halton" | "random" | "philox" (in-kernel counter RNG)
+    noise_sigma: Optional[List[List[float]]] = None
+    noise_mu: Optional[List[float]] = None
+    device: str = "cuda:0"
+    lambda_: float = 1.0
+    update_lambda: bool = False
+    update_cov: bool = False
+    u_min: Optional[List[float]] = None
+    u_max: Optional[List[float]] = None
+    u_init: float = 0.0
+    U_init: Optional[List[List[float]]] = None
+    u_scale: float = 1
+    u_per_command: int = 1
+    rollout_var_discount: float = 0.95
+    sample_null_action: bool = False
+    sample_previous_plan: bool = True
+    sample_other_priors: bool = False
+    noise_abs_cost: bool = False
+    filter_u: bool = False
+    use_priors: bool = False
+    seed_val: int = 0
+    eta_u_bound: int = 10
+    eta_l_bound: int = 5
+
+
+_SEQ_KEYS = ("mean_action", "mean_action_1", "mean_action_2", "best_traj", "best_traj_1", "best_traj_2")
+
+
+class MPPI():
+    def __init__(self, cfg, dynamics: Callable, running_cost: Callable):
+        self.env_type = cfg.env_type
+        self.multi_modal = bool(cfg.multi_modal)
+        self._full_cfg = cfg
+        m = cfg.mppi
+        self.mppi_mode = getattr(m, "mppi_mode", "halton-spline")
+        if self.mppi_mode != "halton-spline":
+            raise NotImplementedError("mppi_mode='simple' is not used by any shipped configuration (mppi/*.yaml:4)")
+        self.sampling_method = getattr(m, "sampling_method", "halton")
+        self.K = int(m.num_samples)
+        self.half_K = int(self.K / 2)
+        self.T = int(m.horizon)
+        self.filter_u = bool(getattr(m, "filter_u", False))
+        self.lambda_ = getattr(m, "lambda_", 1.0)
+        self.sample_null_action = bool(getattr(m, "sample_null_action", False))
+        self.u_per_command = getattr(m, "u_per_command", 1)
+        self.device = "cpu"
+        self.u_scale = float(getattr(m, "u_scale", 1))
+        if not getattr(m, "noise_sigma", None):
+            m.noise_sigma = np.identity(int(m.nx / 2)).tolist()
+        self.noise_sigma = torch.tensor(m.noise_sigma, dtype=torch.float32)
+        self.nx = m.nx
+        self.nu = self.noise_sigma.shape[0]
+        if self.K < 20:
+            raise ValueError("num_samples must be >= 20 (command() takes the top 20 trajectories, mppi.py:248)")
+        if self.filter_u and self.T < 9:
+            raise ValueError("filter_u needs horizon >= 9 (Savitzky-Golay window, mppi.py:190,259)")
+        self.F = dynamics
+        self.running_cost = running_cost
+        self.step_size_mean = 0.98
+        self.gamma = getattr(m, "rollout_var_discount", 0.95)
+        self.sgf_window, self.sgf_order = 9, 2
+        self.seed_val = int(getattr(m, "seed_val", 0))
+        self._delta = None
+        self._delta_uploaded = False
+        self._info = None
+        self.gripper_command = None
+        self.state = None
+
+        owner = getattr(dynamics, "__self__", None)
+        sim = getattr(owner, "sim", None)
+        obj = getattr(owner, "objective", None)
+        from m3p2i_aip.planners.motion_planner.cost_functions import Objective
+        from m3p2i_aip.utils.isaacgym_utils.isaacgym_wrapper import IsaacGymWrapper
+        self.fused = (isinstance(sim, IsaacGymWrapper) and isinstance(obj, Objective)
+                      and getattr(running_cost, "__self__", None) is owner and getattr(m, "fused", True)
+                      and sim.num_envs == self.K)
+        noise_mode = A.NOISE_PHILOX if self.sampling_method == "philox" else A.NOISE_TABLE
+        if self.fused:
+            self._sim, self._objective = sim, obj
+            self.backend = sim.attach_planner(cfg, noise_mode=noise_mode, seed=self.seed_val)
+        else:
+            self._sim, self._objective = None, None
+            scene = S.build_point_scene() if self.env_type == "point_env" else S.build_panda_scene()
+            self.backend = native.NativePlanner(S.build_config(cfg, noise_mode=noise_mode, seed=self.seed_val), scene)
+            # the softmin/update kernels need no scene state, but the handle wants one
+            actors = S.default_actors(self.env_type)
+            self.backend.set_state(S.initial_dof_state(actors), S.initial_root_state(actors))
+
+    # ------------------------------------------------------------------ noise table (mppi.py:386-392,458-483)
+    @property
+    def delta(self):
+        return self._delta
+
+    @delta.setter
+    def delta(self, value):
+        self._delta = value
+        self._delta_uploaded = False
+
+    def get_samples(self, sample_shape, **kwargs):
+        if self.sampling_method == "halton":
+            return torch.from_numpy(mppi_utils.halton_spline_table(sample_shape, self.T, self.nu))
+        if self.sampling_method == "random":
+            g = torch.Generator().manual_seed(self.seed_val)
+            return torch.randn(sample_shape, self.T, self.nu, generator=g) * torch.sqrt(torch.diagonal(self.noise_sigma))
+        raise ValueError(f"unknown sampling_method {self.sampling_method!r}")
+
+    def _ensure_noise(self):
+        if self.sampling_method == "philox" and self._delta is None:
+            return
+        if self.sampling_method == "random" or self._delta is None:
+            self.delta = self.get_samples(self.K, base_seed=0)
+        if not self._delta_uploaded:
+            d = self._delta.detach().cpu().numpy() if torch.is_tensor(self._delta) else np.asarray(self._delta)
+            if self.backend.cfg.noise_mode != A.NOISE_TABLE:
+                raise RuntimeError("a delta table was given but the planner was created with sampling_method='philox'")
+            self.backend.set_noise_table(d)
+            self._delta_uploaded = True
+
+    # ------------------------------------------------------------------ command (mppi.py:211-264)
+    def command(self, state):
+        if not torch.is_tensor(state):
+            state = torch.tensor(state)
+        self.state = state.to(torch.float32)
+        self._ensure_noise()
+        self._lazy = {}
+        if self.fused:
+            obj = self._objective
+            if obj.task is None:
+                raise RuntimeError("Objective.update_objective(task, goal) must be called before command()")
+            self._sim._push()
+            grip = self.gripper_command if self.env_type == "panda_env" else None
+            self.backend.set_objective(obj.task, obj.goal_array(), grip)
+            action, _, info = self.backend.command(want_cost=False)
+            self._sim.mark_device_advanced()
+        else:
+            action, info = self._command_generic()
+        self._info = info
+        return torch.from_numpy(np.array(action, copy=True))
+
+    def _dynamics(self, state, u, t=None):
+        return self.F(state, u, t=None)
+
+    def _running_cost(self, state):
+        return self.running_cost(state)
+
+    def _shift_action(self, seq):
+        out = torch.roll(seq, -1, dims=0)
+        out[-1] = seq[-1]
+        return out
+
+    def _command_generic(self):
+        """mppi.py:237-245,381-416,275-332 with the user's callbacks; update through the native library."""
+        K, T, nu = self.K, self.T, self.nu
+        st = self.backend.get_planner_state()
+        seqs = {k: torch.from_numpy(np.asarray(getattr(st, k)[: T * nu], np.float32).reshape(T, nu).copy()) for k in _SEQ_KEYS}
+        seqs["mean_action"] = self._shift_action(seqs["mean_action"])
+        if self.multi_modal:
+            for k in ("mean_action_1", "mean_action_2", "best_traj_1", "best_traj_2"):
+                seqs[k] = self._shift_action(seqs[k])
+        delta = self._delta if torch.is_tensor(self._delta) else torch.from_numpy(self.backend.get_noise())
+        delta = delta.to(torch.float32).clone()
+        delta[-1] = 0.0
+        scaled = delta * torch.sqrt(torch.diagonal(self.noise_sigma))
+        if self.multi_modal:
+            act = torch.cat((seqs["mean_action_1"] + scaled[:self.half_K], seqs["mean_action_2"] + scaled[self.half_K:]), 0)
+        else:
+            act = seqs["mean_action"] + scaled
+        u_min = torch.tensor(list(self.backend.cfg.u_min)[:nu])
+        u_max = torch.tensor(list(self.backend.cfg.u_max)[:nu])
+        act = torch.max(torch.min(act, u_max), u_min)
+        if self.multi_modal:
+            act[0] = seqs["best_traj_1"]
+            act[self.half_K] = seqs["best_traj_2"]
+        if self.env_type == "panda_env" and self.gripper_command in ("open", "close"):
+            act[:, :, 7:9] = 1.5 if self.gripper_command == "open" else -1.5
+        state = self.state.view(1, -1).repeat(K, 1) if self.state.shape != (K, self.nx) else self.state
+        cost_horizon = torch.zeros(K, T)
+        states, actions = [], []
+        for t in range(T):
+            u = self.u_scale * act[:, t]
+            if self.sample_null_action:
+                u[K - 1] = 0.0
+            state, u = self._dynamics(state, u, t)
+            c = self._running_cost(state)
+            cost_horizon[:, t] = torch.as_tensor(c, dtype=torch.float32)
+            states.append(torch.as_tensor(state, dtype=torch.float32))
+            actions.append(torch.as_tensor(u, dtype=torch.float32))
+        actions = torch.stack(actions, dim=-2)
+        self._lazy["states"] = torch.stack(states, dim=-2)
+        for k in _SEQ_KEYS:
+            getattr(st, k)[: T * nu] = seqs[k].reshape(-1).tolist()
+        self.backend.set_planner_state(st)
+        mean, info = self.backend.update_only(cost_horizon.numpy(), actions.numpy())
+        cs = cost_horizon.sum(1)
+        self._lazy["cost_total"] = cs + cs.mean()
+        self._lazy["actions"] = actions / self.u_scale
+        action = mean
+        if self.filter_u:
+            action = S.savgol_matrix(T) @ mean
+        return action, info
+
+    # ------------------------------------------------------------------ results of the last command (read lazily)
+    def _seq(self, key):
+        st = self.backend.get_planner_state()
+        return torch.from_numpy(np.asarray(getattr(st, key)[: self.T * self.nu], np.float32).reshape(self.T, self.nu).copy())
+
+    def _buf(self, name, which):
+        if name not in self._lazy:
+            self._lazy[name] = torch.from_numpy(self.backend.read_buffer(which))
+        return self._lazy[name]
+
+    mean_action = property(lambda s: s._seq("mean_action"))
+    mean_action_1 = property(lambda s: s._seq("mean_action_1"))
+    mean_action_2 = property(lambda s: s._seq("mean_action_2"))
+    best_traj = property(lambda s: s._seq("best_traj"))
+    best_traj_1 = property(lambda s: s._seq("best_traj_1"))
+    best_traj_2 = property(lambda s: s._seq("best_traj_2"))
+
+    @property
+    def beta(self):
+        return self.backend.get_planner_state().beta
+
+    @property
+    def weights(self):
+        return self._buf("weights3", A.BUF_WEIGHTS)[0]
+
+    @property
+    def weights_1(self):
+        return self._buf("weights3", A.BUF_WEIGHTS)[1, :self.half_K]
+
+    @property
+    def weights_2(self):
+        return self._buf("weights3", A.BUF_WEIGHTS)[2, self.half_K:]
+
+    @property
+    def states(self):
+        return self._buf("states", A.BUF_STATES)
+
+    @property
+    def actions(self):
+        return self._buf("actions", A.BUF_ACTIONS)
+
+    @property
+    def cost_total(self):
+        if "cost_total" not in self._lazy:
+            self._lazy["cost_total"] = torch.from_numpy(np.array(self.backend.fetch_result(want_cost=True)[1], copy=True))
+        return self._lazy["cost_total"]
+
+    def _topk(self):
+        if "top" not in self._lazy:
+            idx, w, _ = self.backend.top_trajs(20)
+            if self.fused:
+                _, _, tr = self.backend.top_trajs(20)
+            else:
+                tr = self._lazy["states"][torch.from_numpy(idx.astype(np.int64))][:, :, [0, 2]].numpy()
+            self._lazy["top"] = (torch.from_numpy(idx.astype(np.int64)), torch.from_numpy(w), torch.from_numpy(np.array(tr)))
+        return self._lazy["top"]
+
+    top_idx = property(lambda s: s._topk()[0])
+    top_values = property(lambda s: s._topk()[1])
+    top_trajs = property(lambda s: s._topk()[2])

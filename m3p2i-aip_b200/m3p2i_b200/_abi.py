@@ -138,8 +138,8 @@ PROTOTYPES = {
 
 
 def bind(lib, prototypes=PROTOTYPES, prefix_from="m3p2i_", prefix_to=None, skip=()):
-    """Attach restype/argtypes. With prefix_to, binds the same signatures under another prefix (the oracle's
-    orc_* functions share the argument lists of their m3p2i_* counterparts)."""
+    """Attach restype/argtypes. With prefix_to, binds the same signatures under another symbol prefix (used by
+    test doubles that export the same argument lists)."""
     out = {}
     for name, (res, args) in prototypes.items():
         if name in skip:

@@ -135,6 +135,16 @@ int orc_set_state(Oracle* o, const float* dof, const float* root) {
   if (!o || !dof || !root || !o->have_scene) return -1;
   memcpy(o->dof0, dof, sizeof(float) * 2 * o_ndof(o));
   memcpy(o->root0, root, sizeof(float) * 13 * o_nactors(o));
+  /* movable bodies that the integrator keeps fixed (the floating dyn-obs plate) follow the real state */
+  {
+    const int ns = o->cfg.env_type == M3P2I_ENV_POINT ? o->ps.n_static : o->qs.n_static;
+    M3P2IBox* st = o->cfg.env_type == M3P2I_ENV_POINT ? o->ps.statics : o->qs.statics;
+    for (int k = 0; k < ns; ++k)
+      if (st[k].actor >= 0 && st[k].actor < o_nactors(o)) {
+        memcpy(st[k].pos, root + 13 * st[k].actor, 12);
+        memcpy(st[k].quat, root + 13 * st[k].actor + 3, 16);
+      }
+  }
   o->have_state = 1;
   o->env_live = 0;
   return 0;

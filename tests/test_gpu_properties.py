@@ -1,0 +1,147 @@
+"""Size-independent properties of the CUDA path at the full BASELINE.json sizes (the oracle is too slow there to
+be the checker for every element; it still checks a strided subset of samples)."""
+import numpy as np
+import pytest
+
+import oracle_py as O
+from helpers import assert_close, make_backend
+from m3p2i_b200 import _abi as A
+from m3p2i_b200 import native
+from m3p2i_b200 import scene as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _c4(K=4096, T=32, task="pick", mm=False, noise=A.NOISE_PHILOX, K_local=None, offset=0):
+    cfg = S.make_cfg("panda_env", task, None, K, T, multi_modal=mm)
+    actors = S.default_actors("panda_env")
+    dof, root = S.initial_dof_state(actors).copy(), S.initial_root_state(actors).copy()
+    root[S.actor_index(actors, "cubeA"), 2] -= 0.0095
+    root[S.actor_index(actors, "cubeB"), 2] -= 0.0095
+    cb = root[S.actor_index(actors, "cubeB")]
+    goal = np.concatenate([cb[:3] + np.array([0, 0, 0.055], np.float32), cb[3:7]])
+    n = make_backend(native.NativePlanner, cfg, noise_mode=noise, seed=11, K_local=K_local, offset=offset)
+    n.set_state(dof, root)
+    n.set_objective(task, goal, {"pick": "close", "reach": "open"}[task])
+    return cfg, n, (dof, root, goal)
+
+
+def test_c4_invariants():
+    cfg, n, _ = _c4()
+    K, T, nu = n.K, n.T, n.nu
+    action, cost_total, info = n.command()
+    acts, states = n.read_buffer(A.BUF_ACTIONS), n.read_buffer(A.BUF_STATES)
+    ch, w = n.read_buffer(A.BUF_COST_HORIZON), n.read_buffer(A.BUF_WEIGHTS)
+    # bounds, gripper override, null action (mppi.py:300-302,405,412-416)
+    lo, hi = np.asarray(cfg.mppi.u_min, np.float32), np.asarray(cfg.mppi.u_max, np.float32)
+    assert (acts >= lo - 1e-6).all() and (acts <= hi + 1e-6).all()
+    assert (acts[:-1, :, 7:] == -1.5).all()
+    assert (acts[-1] == 0).all()
+    # cost_total = sum_t c + mean_k sum_t c (mppi.py:282-284,325)
+    cs = ch.sum(1, dtype=np.float64)
+    assert_close(cost_total, cs + cs.mean(), 1e-5, 1e-3, "cost_total quirk")
+    # weights: softmin of the discounted cost (mppi.py:435-442)
+    J = n.read_buffer(A.BUF_COST_DISC)
+    g = 0.95 ** np.arange(T)
+    assert_close(J, (ch.astype(np.float64) * g).sum(1), 1e-5, 1e-4, "discounted cost")
+    assert w[0].sum() == pytest.approx(1.0, abs=1e-4)
+    assert int(np.argmax(w[0])) == int(np.argmin(J)) == info.best_idx[0]
+    e = np.exp(-(J.astype(np.float64) - J.min()) / info.beta[0])
+    assert_close(w[0], e / e.sum(), 1e-3, 1e-7, "weights")
+    # mean update (mppi.py:498-503), first call: old mean is zero
+    new_mean = (w[0][:, None, None].astype(np.float64) * acts).sum(0)
+    st = n.get_planner_state()
+    mean = np.asarray(st.mean_action[: T * nu], np.float32).reshape(T, nu)
+    assert_close(mean, 0.98 * new_mean, 1e-4, 1e-5, "mean_action")
+    best = np.asarray(st.best_traj[: T * nu], np.float32).reshape(T, nu)
+    assert np.array_equal(best, acts[info.best_idx[0]])
+    # filtered action = S @ mean (mppi.py:257-263)
+    assert_close(action, S.savgol_matrix(T) @ mean, 1e-4, 1e-5, "savgol")
+    # joints stay inside the URDF limits, states are joint 1/2 rows
+    assert (np.abs(states[:, :, 1]) <= 2.175 + 1e-5).all() and (np.abs(states[:, :, 3]) <= 2.175 + 1e-5).all()
+    assert np.isfinite(cost_total).all()
+    n.close()
+
+
+def test_c4_deterministic_and_shift():
+    _, a, _ = _c4()
+    _, b, _ = _c4()
+    for _ in range(3):
+        ra, rb = a.command(), b.command()
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+    a.close()
+    b.close()
+
+
+def test_c4_strided_samples_match_oracle():
+    """Every 64th sample of the K=4096 x H=32 pick rollout against the oracle run on just those samples."""
+    O.set_threads(8)
+    cfg, n, (dof, root, goal) = _c4()
+    n.command()
+    acts = n.read_buffer(A.BUF_ACTIONS)
+    ch = n.read_buffer(A.BUF_COST_HORIZON)
+    states = n.read_buffer(A.BUF_STATES)
+    sel = np.arange(0, 4096, 64)
+    ocfg = S.make_cfg("panda_env", "pick", None, len(sel), 32)
+    o = make_backend(O.Oracle, ocfg)
+    o.set_state(dof, root)
+    o.set_objective("pick", goal, "close")
+    # open-loop replay of the exact actions the kernel drew (sample K-1 is not in the subset: no null action here)
+    ocfg.mppi.sample_null_action = False
+    o2 = make_backend(O.Oracle, ocfg)
+    o2.set_state(dof, root)
+    o2.set_objective("pick", goal, "close")
+    s_o, c_o = o2.rollout_actions(acts[sel])
+    assert_close(states[sel], s_o, 1e-3, 1e-3, "states", 0.005)
+    assert_close(ch[sel], c_o, 1e-3, 1e-3, "cost_horizon", 0.005)
+    o.close(); o2.close(); n.close()
+
+
+@pytest.mark.parametrize("task,mm", [("pick", False), ("reach", True)])
+def test_shard_invariance(task, mm):
+    """K split over 2 and 4 shards (host-staged phases on one GPU): per-sample costs are bit-identical to the
+    unsharded run (Philox counters use the global sample id), the action agrees to reduction order."""
+    K, T = 2048, 16
+    _, full, _ = _c4(K, T, task, mm)
+    a_full, c_full, _ = full.command()
+    a_full, c_full = a_full.copy(), c_full.copy()
+    J_full = full.read_buffer(A.BUF_COST_DISC)
+    for nshard in (2, 4):
+        Kl = K // nshard
+        shards = [_c4(K, T, task, mm, K_local=Kl, offset=r * Kl)[1] for r in range(nshard)]
+        J = np.concatenate([s.phase_rollout() for s in shards])
+        assert np.array_equal(J, J_full)
+        parts = sum(s.phase_partials(J) for s in shards)
+        outs = [s.phase_finish(parts) for s in shards]
+        for r, (a, c, info) in enumerate(outs):
+            assert_close(a, a_full, 1e-5, 1e-6, f"action shard {r}/{nshard}")
+            assert_close(c, c_full[r * Kl:(r + 1) * Kl], 1e-6, 1e-4, f"cost_total shard {r}/{nshard}")
+        for s in shards:
+            s.close()
+    full.close()
+
+
+def test_table_and_philox_agree():
+    """Feeding the dumped Philox table back in table mode gives the same rollout."""
+    _, p, _ = _c4(1024, 16)
+    _, t, _ = _c4(1024, 16, noise=A.NOISE_TABLE)
+    t.set_noise_table(p.get_noise())
+    rp, rt = p.command(), t.command()
+    assert_close(rt[1], rp[1], 1e-6, 1e-5, "cost_total")
+    assert_close(rt[0], rp[0], 1e-6, 1e-6, "action")
+    p.close(); t.close()
+
+
+def test_errors_are_loud():
+    cfg = S.make_cfg("point_env", "navigation", [1.0, 1.0], 64, 12)
+    c = S.build_config(cfg)
+    n = native.NativePlanner(c, S.build_point_scene())
+    with pytest.raises(native.NativeError, match="set_state"):
+        n.command()
+    with pytest.raises(native.NativeError, match="task"):
+        n.set_objective("pick", [0.0] * 7)
+    bad = S.build_config(cfg)
+    bad.nu = 3
+    with pytest.raises(native.NativeError, match="nu"):
+        native.NativePlanner(bad, S.build_point_scene())
+    n.close()
