@@ -212,6 +212,8 @@ typedef struct M3P2ICommandInfo {
   float kernel_ms;    /* device time of the command's kernels (CUDA events on the handle's stream) */
   int32_t launches;   /* kernels launched by this command */
   int32_t beta_iters; /* iterations of the on-the-fly beta search (m3p2i.py:30-43), summed over sets */
+  float rollout_ms;   /* device time of the fused rollout kernel alone (the roofline figure is computed from it) */
+  float reserved;
 } M3P2ICommandInfo;
 
 typedef struct M3P2IHandle_* m3p2i_handle;

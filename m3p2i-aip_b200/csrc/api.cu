@@ -84,7 +84,7 @@ struct M3P2IHandle_ {
   M3P2IConfig cfg;
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr = nullptr;
   bool have_scene = false, have_state = false, env_live = false, env_alloc = false, base_dirty = false;
   M3P2IPointScene ps_in;
   M3P2IPandaScene qs_in;
@@ -101,7 +101,7 @@ struct M3P2IHandle_ {
   DevBuf<PandaRef> refs;
   DevBuf<Stats> stats;
   DevBuf<M3P2ICommandInfo> info;
-  bool have_noise = false, have_row0 = false, have_filt = false;
+  bool have_noise = false, have_row0 = false, have_filt = false, have_evr = false;
   // pinned host staging
   float* pin = nullptr;
   size_t pin_n = 0;
@@ -391,10 +391,11 @@ int fetch(H* h, float* out_action, float* out_cost_total, M3P2ICommandInfo* info
   CK(cudaStreamSynchronize(h->stream));
   if (out_action) memcpy(out_action, unfiltered ? p + TN : p, sizeof(float) * TN);
   if (out_cost_total) memcpy(out_cost_total, pc, sizeof(float) * K);
-  const float kms = h->last_info.kernel_ms;
+  const float kms = h->last_info.kernel_ms, rms = h->last_info.rollout_ms;
   const int nl = h->last_info.launches;
   h->last_info = *pi;
   h->last_info.kernel_ms = kms;
+  h->last_info.rollout_ms = rms;
   h->last_info.launches = nl;
   if (info) *info = h->last_info;
   return 0;
@@ -406,6 +407,8 @@ int command_device(H* h) {
   int launches = 0;
   CK(cudaEventRecord(h->ev0, h->stream));
   if ((rc = run_rollout(h, &launches, nullptr))) return rc;
+  CK(cudaEventRecord(h->evr, h->stream));
+  h->have_evr = true;
   if ((rc = gather_J(h))) return rc;
   if ((rc = run_update(h, 1, &launches))) return rc;
   if ((rc = reduce_partials(h))) return rc;
@@ -419,6 +422,12 @@ int finish_timing(H* h) {
   float ms = 0.0f;
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_info.kernel_ms = ms;
+  h->last_info.rollout_ms = 0.0f;
+  if (h->have_evr) {
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->evr));
+    h->last_info.rollout_ms = ms;
+    h->have_evr = false;
+  }
   return 0;
 }
 
@@ -478,6 +487,7 @@ int m3p2i_create(const M3P2IConfig* cfg, int device, m3p2i_handle* out) {
   h->stream = h->own_stream;
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->evr);
   if (e == cudaSuccess) e = h->seq.alloc(SEQ_COUNT * TN);
   if (e == cudaSuccess) e = h->base.alloc(64);
   if (e == cudaSuccess) e = h->actions.alloc(K * TN);
@@ -523,6 +533,7 @@ void m3p2i_destroy(m3p2i_handle h) {
   if (h->pin) cudaFreeHost(h->pin);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->evr) cudaEventDestroy(h->evr);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -715,7 +726,9 @@ int m3p2i_command_resident(m3p2i_handle h, M3P2ICommandInfo* info) {
 
 int m3p2i_fetch_result(m3p2i_handle h, float* out_action, float* out_cost_total) {
   if (!h) return fail(M3P2I_ERR_ARG, "null handle");
-  return fetch(h, out_action, out_cost_total, nullptr, false);
+  int rc = fetch(h, out_action, out_cost_total, nullptr, false);
+  if (rc) return rc;
+  return finish_timing(h);
 }
 
 int m3p2i_rollout_actions(m3p2i_handle h, const float* actions, float* out_states, float* out_cost_h) {

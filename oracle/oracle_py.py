@@ -67,7 +67,10 @@ class Oracle:
         from m3p2i_b200 import scene as S
         if cfg is None:
             cfg = S.sim_only_cfg(sim.env_type, sim.num_envs, sim.cfg)
-        return cls(S.build_config(cfg, noise_mode=noise_mode, seed=seed), sim.scene)
+        o = cls(S.build_config(cfg, noise_mode=noise_mode, seed=seed), sim.scene)
+        if getattr(cfg.mppi, "filter_u", False) and cfg.mppi.horizon >= 9:
+            o.set_filter_matrix(S.savgol_matrix(int(cfg.mppi.horizon)))
+        return o
 
     def __init__(self, config, scene):
         self.L = lib()
@@ -135,11 +138,15 @@ class Oracle:
         s = None if S is None else _f32(S)
         self._ck(self.L.fn["m3p2i_set_filter_matrix"](self.h, A.as_fp(s)), "set_filter_matrix")
 
-    def command(self):
+    def fetch_result(self, want_cost=True):
+        return None, self._last_cost
+
+    def command(self, want_cost=True):
         act = np.empty((self.T, self.nu), np.float32)
         cost = np.empty(self.K, np.float32)
         info = A.CommandInfo()
         self._ck(self.L.fn["m3p2i_command"](self.h, A.as_fp(act), A.as_fp(cost), C.byref(info)), "command")
+        self._last_cost = cost
         return act, cost, info
 
     def rollout_actions(self, actions):
@@ -190,7 +197,7 @@ class Oracle:
         self._ck(self.L.fn["m3p2i_phase_partials"](self.h, A.as_fp(J), A.as_fp(out)), "phase_partials")
         return out
 
-    def phase_finish(self, partials_sum):
+    def phase_finish(self, partials_sum, want_cost=True):
         p = _f32(partials_sum)
         act = np.empty((self.T, self.nu), np.float32)
         cost = np.empty(self.K, np.float32)

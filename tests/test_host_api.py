@@ -1,0 +1,122 @@
+"""Host-side mirror of the reference API (m3p2i_aip.* module paths) driven exactly like scripts/reactive_tamp.py.
+
+CPU part: the mirror classes run on the oracle backend (injected through backend_factory) and must reproduce the
+reference goldens -- this checks the host logic (state push, objective / gripper plumbing, lazily read results).
+GPU part (-m gpu): the same with the native CUDA backend, fused and generic paths.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle_py as O
+from helpers import GRIPPER, assert_close, case_cfg, golden_cases, load_golden
+from m3p2i_aip.planners.motion_planner import m3p2i
+from m3p2i_aip.planners.motion_planner.cost_functions import Objective
+from m3p2i_aip.utils.isaacgym_utils import isaacgym_wrapper as wrapper
+
+
+class Tamp:
+    """scripts/reactive_tamp.py:21-73 (REACTIVE_TAMP) on this repo's modules."""
+
+    def __init__(self, cfg, backend_factory=None, fused=True):
+        self.sim = wrapper.IsaacGymWrapper(cfg.isaacgym, cfg.env_type, num_envs=cfg.mppi.num_samples, viewer=False,
+                                           device=cfg.mppi.device, cube_on_shelf=cfg.cube_on_shelf,
+                                           backend_factory=backend_factory)
+        self.cfg = cfg
+        self.objective = Objective(cfg)
+        cfg.mppi.fused = fused
+        self.motion_planner = m3p2i.M3P2I(cfg, dynamics=self.dynamics, running_cost=self.running_cost)
+
+    def dynamics(self, _, u, t=None):
+        self.sim.set_dof_velocity_target_tensor(u)
+        self.sim.step()
+        states = torch.stack([self.sim.robot_pos[:, 0], self.sim.robot_vel[:, 0], self.sim.robot_pos[:, 1],
+                              self.sim.robot_vel[:, 1]], dim=1)
+        return states, u
+
+    def running_cost(self, _):
+        return self.objective.compute_cost(self.sim)
+
+    def run_tamp(self, dof_state, root_state, task, goal, extra_step):
+        self.sim._dof_state[:] = dof_state
+        self.sim._root_state[:] = root_state
+        self.sim.set_dof_state_tensor(self.sim._dof_state)
+        self.sim.set_actor_root_state_tensor(self.sim._root_state)
+        if extra_step:
+            self.sim.step()
+        self.motion_planner.update_gripper_command(task)
+        self.objective.update_objective(task, goal)
+        return self.motion_planner.command(self.sim._dof_state[0])
+
+
+def _replay(name, backend_factory, fused, rtol, atol, bad=0.0):
+    g = load_golden(name)
+    cfg = case_cfg(g)
+    tamp = Tamp(cfg, backend_factory, fused)
+    mp = tamp.motion_planner
+    assert mp.fused == fused
+    mp.delta = torch.from_numpy(g["delta"].copy())
+    task = str(g["task"])
+    for i in range(int(g["calls"])):
+        action = tamp.run_tamp(torch.from_numpy(g[f"dof_{i}"]), torch.from_numpy(g[f"root_{i}"]), task,
+                               torch.from_numpy(g["goal"]), bool(g["extra_step"]))
+        assert_close(action.numpy(), g[f"action_{i}"], rtol, atol, f"{name}[{i}] action")
+        assert_close(mp.mean_action.numpy(), g[f"mean_action_{i}"], rtol, atol, f"{name}[{i}] mean_action")
+        assert_close(mp.cost_total.numpy(), g[f"cost_total_{i}"], rtol, 5 * atol, f"{name}[{i}] cost_total", bad)
+        assert_close(mp.weights.numpy(), g[f"weights_{i}"], 2e-2, 1e-5, f"{name}[{i}] weights", bad)
+        assert_close(mp.states.numpy(), g[f"states_{i}"], rtol, atol, f"{name}[{i}] states", bad)
+        assert_close(mp.actions.numpy(), g[f"actions_{i}"], rtol, atol, f"{name}[{i}] actions")
+        assert mp.top_trajs.shape == g[f"top_trajs_{i}"].shape
+        if bool(g["multi_modal"]):
+            assert mp.get_pull_preference() == int(g[f"pull_preference_{i}"])
+            assert_close(mp.mean_action_1.numpy(), g[f"mean_action_1_{i}"], rtol, atol, f"{name}[{i}] mean_action_1")
+            assert_close(mp.best_traj_2.numpy(), g[f"best_traj_2_{i}"], rtol, atol, f"{name}[{i}] best_traj_2")
+    tamp.sim.stop_sim()
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_mirror_api_on_oracle_backend(name):
+    _replay(name, O.Oracle.for_sim, True, 2e-4, 2e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", golden_cases())
+def test_mirror_api_fused_native(name):
+    contact = name in ("nav_obstacle", "push_k256_t20", "pull_k256_t20", "push_pull_mm", "panda_pick")
+    _replay(name, None, True, 1e-2, 1e-2, 0.02 if contact else 0.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["nav_k200_t12", "pull_k256_t20", "push_pull_mm", "panda_reach", "panda_pick"])
+def test_mirror_api_generic_callbacks_native(name):
+    """Python callbacks invoked T times per command (the reference's loop), update through m3p2i_update_only."""
+    contact = name in ("pull_k256_t20", "push_pull_mm", "panda_pick")
+    _replay(name, None, False, 1e-2, 1e-2, 0.02 if contact else 0.0)
+
+
+def test_objective_validates_task():
+    from m3p2i_b200 import scene as S
+    obj = Objective(S.make_cfg("point_env", "push", [0.0, 0.0], 32, 12))
+    with pytest.raises(ValueError, match="unknown task"):
+        obj.update_objective("fly", [0.0, 0.0])
+
+
+def test_planner_argument_checks():
+    from m3p2i_b200 import scene as S
+    cfg = S.make_cfg("point_env", "navigation", [1.0, 1.0], 10, 12)
+    t = None
+    with pytest.raises(ValueError, match=">= 20"):
+        t = Tamp(cfg, O.Oracle.for_sim)
+    cfg = S.make_cfg("point_env", "navigation", [1.0, 1.0], 32, 8)
+    with pytest.raises(ValueError, match="horizon >= 9"):
+        t = Tamp(cfg, O.Oracle.for_sim)
+    assert t is None
+
+
+def test_halton_spline_table_shape_and_determinism():
+    from m3p2i_aip.utils import mppi_utils
+    a = mppi_utils.halton_spline_table(24, 12, 2)
+    b = mppi_utils.halton_spline_table(24, 12, 2)
+    assert a.shape == (24, 12, 2) and np.array_equal(a, b) and np.isfinite(a).all()
+    h = mppi_utils.generate_halton_samples(8, 2)
+    assert np.allclose(h[:3, 0], [0.5, 0.25, 0.75]) and np.allclose(h[:3, 1], [1 / 3, 2 / 3, 1 / 9])
