@@ -200,7 +200,10 @@ def main():
     dof, root, goal = scene_inputs()
     planner.set_objective("pick", goal, "close")
     planner.set_state(dof, root)
-    stream = torch.cuda.current_stream()
+    # a stream torch owns, so that torch.cuda.Event brackets exactly the stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     planner.set_stream(stream.cuda_stream)
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 

@@ -1,5 +1,7 @@
 // kernels.cu — the MPPI hot path on sm_100a: fused sample -> rollout -> cost kernel, softmin statistics,
 // weighted action sums, mean update. One thread owns one sample trajectory; all HBM traffic is sample-fastest SoA.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "panda_env.cuh"
 #include "point_env.cuh"
@@ -135,18 +137,32 @@ __global__ void k_refs(const __grid_constant__ RolloutCfg c, const __grid_consta
   }
 }
 
+// Threads per CTA of the rollout kernel. The kernel is latency-bound (one serial chain per sample), so small CTAs
+// that spread the samples over all 148 SMs win; M3P2I_ROLLOUT_BLOCK overrides the choice (8..32) for experiments.
+static int rollout_block(int K) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("M3P2I_ROLLOUT_BLOCK");
+    forced = e ? atoi(e) : 0;
+    if (forced != 0 && (forced < 1 || forced > kRolloutBlock)) forced = 0;
+  }
+  if (forced) return forced;
+  return K <= 148 * 16 * 4 ? 16 : kRolloutBlock;
+}
+
 void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp,
                     const RolloutBufs& b, bool need_refs, cudaStream_t st, int* launches) {
-  const int grid = (c.K + kRolloutBlock - 1) / kRolloutBlock;
+  const int block = rollout_block(c.K);
+  const int grid = (c.K + block - 1) / block;
   if (env_type == M3P2I_ENV_POINT) {
-    k_rollout<M3P2I_ENV_POINT><<<grid, kRolloutBlock, 0, st>>>(c, *pp, b);
+    k_rollout<M3P2I_ENV_POINT><<<grid, block, 0, st>>>(c, *pp, b);
     ++*launches;
   } else {
     if (need_refs) {
       k_refs<<<1, 32, 0, st>>>(c, *qp, b);
       ++*launches;
     }
-    k_rollout<M3P2I_ENV_PANDA><<<grid, kRolloutBlock, 0, st>>>(c, *qp, b);
+    k_rollout<M3P2I_ENV_PANDA><<<grid, block, 0, st>>>(c, *qp, b);
     ++*launches;
   }
 }

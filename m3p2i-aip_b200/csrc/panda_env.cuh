@@ -203,6 +203,40 @@ DEV V3 solve_contact3(Dyn3& A, Dyn3& B, V3 n, float depth, V3 c, float mu, float
   return Pn + Pt;
 }
 
+// The same contact equations for the hot pair type, a free cube against a fixed box: every term of the fixed body
+// vanishes, r x P is reused from r x n / r x t. Returns the impulse on the cube.
+DEV V3 solve_cube_static(V3& v, V3& w, float im, float ii, V3 x, V3 n, float depth, V3 c, float mu, float h,
+                         const PandaParams& P) {
+  const V3 ra = c - x;
+  V3 va = v + cross(w, ra);
+  float vn = dot(va, n);
+  const V3 rn = cross(ra, n);
+  const float kn = im + ii * dot(rn, rn);
+  float target;
+  if (depth > 0.0f) {
+    const float pen = fmaxf(depth - P.slop, 0.0f);
+    target = fminf(P.baumgarte * pen / h, P.max_corr_vel);
+  } else {
+    target = depth / h;
+  }
+  const float jn = (target - vn) / kn;
+  if (jn <= 0.0f) return mk(0, 0, 0);
+  v = v + (jn * im) * n;
+  w = w + (jn * ii) * rn;
+  va = v + cross(w, ra);
+  vn = dot(va, n);
+  V3 t = va - vn * n;
+  const float vt = sqrtf(dot(t, t));
+  if (vt < 1e-9f) return jn * n;
+  t = (1.0f / vt) * t;
+  const V3 rt = cross(ra, t);
+  const float kt = im + ii * dot(rt, rt);
+  const float jt = fminf(vt / kt, mu * jn);
+  v = v - (jt * im) * t;
+  w = w - (jt * ii) * rt;
+  return jn * n - jt * t;
+}
+
 struct OBox3 {
   V3 c;
   M33 R;
@@ -345,16 +379,35 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
       C[i].im = 1.0f / P.cube_mass[i]; C[i].ii = 1.0f / P.cube_inertia[i];
       C[i].axis = mk(0, 0, 0); C[i].slide = 0.0f; C[i].ims = 0.0f;
     }
+    // Positions are fixed during a sub-step, so which cube corners touch which fixed box is decided once (pass 0)
+    // and remembered as one bit per (fixed box, corner); later passes revisit only those corners.
+    unsigned long long hit[2] = {0ull, 0ull};
     for (int p = 0; p < passes; ++p) {
 #pragma unroll
       for (int i = 0; i < 2; ++i)
         for (int k = 0; k < P.n_static; ++k) {
+          unsigned m;
+          if (p == 0) {
+            m = 0u;
+            const OBox3 sb = obox_of(P.st[k]);
+            if (boxes_near(cbox[i], sb, P.contact_margin)) m = 0xffu;
+          } else {
+            m = (unsigned)(hit[i] >> (8 * k)) & 0xffu;
+          }
+          if (!m) continue;
           const OBox3 sb = obox_of(P.st[k]);
-          Dyn3 S;
-          S.v = mk(0, 0, 0); S.w = mk(0, 0, 0); S.x = sb.c; S.im = 0.0f; S.ii = 0.0f;
-          S.axis = mk(0, 0, 0); S.slide = 0.0f; S.ims = 0.0f;
+          const float mu = 0.5f * (P.cube_mu[i] + P.st[k].mu);
           V3 accS = mk(0, 0, 0);
-          box_vs_box3<false>(C[i], cbox[i], S, sb, 0.5f * (P.cube_mu[i] + P.st[k].mu), h, P, accS);
+          unsigned found = 0u;
+          for (int c = 0; c < 8; ++c) {
+            if (!((m >> c) & 1u)) continue;
+            const V3 pt = box_corner(cbox[i], c);
+            V3 n; float depth;
+            if (!point_in_box(pt, sb, P.contact_margin, n, depth)) continue;
+            found |= 1u << c;
+            accS = accS - solve_cube_static(C[i].v, C[i].w, C[i].im, C[i].ii, C[i].x, n, depth, pt, mu, h, P);
+          }
+          if (p == 0) hit[i] |= (unsigned long long)found << (8 * k);
           if (k == P.idx_table) imp_table = imp_table + accS;
           if (k == P.idx_shelf) imp_shelf = imp_shelf + accS;
           if (i == 1) imp_cubeb = imp_cubeb - accS;

@@ -102,9 +102,10 @@ DEV void solve_contact2(Dyn2& A, Dyn2& B, float nx, float ny, float depth, float
 DEV void disc_vs_box(Dyn2& A, float r, Dyn2& B, const OBox2& bx, float mu, float h, const PointParams& P, float& accBx,
                      float& accBy) {
   const float ox = A.x - bx.cx, oy = A.y - bx.cy;
-  const float reach = r + P.contact_margin + sqrtf(bx.hx * bx.hx + bx.hy * bx.hy);
-  if (ox * ox + oy * oy > reach * reach) return;
   const float dx = bx.c * ox + bx.s * oy, dy = -bx.s * ox + bx.c * oy;
+  // broad phase in the box frame (exact for long thin walls, whose bounding circle would always pass)
+  const float reach = r + P.contact_margin;
+  if (fabsf(dx) - bx.hx > reach || fabsf(dy) - bx.hy > reach) return;
   const float qx = clampf(dx, -bx.hx, bx.hx), qy = clampf(dy, -bx.hy, bx.hy);
   float nlx, nly, depth, plx, ply;
   if (qx == dx && qy == dy) {  // centre inside the box: push out along the least-penetration face
@@ -155,9 +156,14 @@ DEV void corners_vs_box(Dyn2& A, const OBox2& ba, Dyn2& B, const OBox2& bb, floa
 // (A, ba) vs (B, bb): corners of A in B, then corners of B in A. acc* accumulate the impulses received.
 DEV void box_vs_box(Dyn2& A, const OBox2& ba, Dyn2& B, const OBox2& bb, float mu, float h, const PointParams& P,
                     float& accAx, float& accAy, float& accBx, float& accBy) {
+  // broad phase: bounding circle of ba against the box bb in bb's frame. Any contact of either direction (a corner
+  // within the margin of the other box) implies dist(centre of ba, bb) <= radius(ba) + margin, so this never drops a
+  // pair the corner tests would have found, and unlike a circle-circle test it rejects the 8 m long walls.
   const float ox = ba.cx - bb.cx, oy = ba.cy - bb.cy;
-  const float reach = sqrtf(ba.hx * ba.hx + ba.hy * ba.hy) + sqrtf(bb.hx * bb.hx + bb.hy * bb.hy) + P.contact_margin;
-  if (ox * ox + oy * oy > reach * reach) return;
+  const float dx = bb.c * ox + bb.s * oy, dy = -bb.s * ox + bb.c * oy;
+  const float reach = sqrtf(ba.hx * ba.hx + ba.hy * ba.hy) + P.contact_margin;
+  const float ex = fmaxf(fabsf(dx) - bb.hx, 0.0f), ey = fmaxf(fabsf(dy) - bb.hy, 0.0f);
+  if (ex * ex + ey * ey > reach * reach) return;
   corners_vs_box<false>(A, ba, B, bb, mu, h, P, accAx, accAy, accBx, accBy);
   corners_vs_box<true>(B, bb, A, ba, mu, h, P, accBx, accBy, accAx, accAy);
 }
@@ -242,7 +248,7 @@ DEV void point_dist(const PointEnv& e, const float* goal, float& dist_cost, floa
 DEV float point_push_cost(const PointEnv& e, const float* goal) {
   float dc, ct;
   point_dist(e, goal, dc, ct);
-  return 3.0f * dc + fmaxf(ct, 0.0f) * 1.0f + (ct > 0.0f ? 0.0f : 0.0f);
+  return 3.0f * dc + 1.0f * fmaxf(ct, 0.0f);
 }
 
 // pull cost; arms the suction force pair for the next step (cost_functions.py:62-89, skill_utils.py:59-94)

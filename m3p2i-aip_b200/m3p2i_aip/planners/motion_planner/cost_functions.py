@@ -36,6 +36,10 @@ class Objective(object):
     def compute_cost(self, sim):
         if self.task is None:
             raise RuntimeError("update_objective(task, goal) must be called before compute_cost")
+        if not getattr(sim, "_has_planner_cfg", False):
+            # the sim was created from the isaacgym section alone (reactive_tamp.py:23-30); the cost kernels also
+            # need kp_suction / multi_modal / pre_height_diff of the full configuration
+            sim.attach_planner(self.cfg)
         sim._push()
         sim.backend.set_objective(self.task, self.goal_array(), None)
         cost = torch.from_numpy(sim.backend.sim_cost())

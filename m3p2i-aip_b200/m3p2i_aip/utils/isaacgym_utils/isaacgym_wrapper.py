@@ -77,13 +77,17 @@ class IsaacGymWrapper:
     def attach_planner(self, cfg, noise_mode=A.NOISE_TABLE, seed=0):
         """Called by the planner (MPPI.__init__) when its callbacks are bound to this sim: re-creates the backend
         with the full planner configuration so that rollout and update run fused on the same K environments."""
+        old = self.backend
         self._refresh()
         if self._backend_factory is not None:
             self.backend = self._backend_factory(self, cfg, noise_mode, seed)
         else:
             from m3p2i_b200 import native
             self.backend = native.NativePlanner.for_sim(self, cfg, noise_mode=noise_mode, seed=seed)
+        if old is not None and old is not self.backend and hasattr(old, "close"):
+            old.close()
         self._push_pending = True
+        self._has_planner_cfg = True
         return self.backend
 
     def _ensure_backend(self):
