@@ -102,7 +102,8 @@ typedef struct M3P2IConfig {
   int32_t sample_offset;       /* global id of local sample 0 */
   int32_t substeps;            /* IsaacGymConfig.substeps (isaacgym_wrapper.py:10) */
   int32_t solver_passes;       /* contact solver sweeps per substep (our integrator; default 2) */
-  int32_t lanes_per_sample;    /* 1 = one thread per sample; reserved for lane-cooperative kernels */
+  int32_t lanes_per_sample;    /* rollout kernel shape: 0 = library chooses, 1 = one thread per sample,
+                                  16 = lane-cooperative team of 16 lanes per sample (panda_env) */
   int32_t reserved_i[3];
   float dt;                    /* cfg.isaacgym.dt */
   float gamma;                 /* cfg.mppi.rollout_var_discount (mppi.py:181) */

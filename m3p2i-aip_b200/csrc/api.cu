@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -99,6 +100,8 @@ struct M3P2IHandle_ {
       weights, partials, filt, cost_total, result, links, scratch;
   DevBuf<float4> states;
   DevBuf<PandaRef> refs;
+  DevBuf<unsigned> ref_flags;
+  unsigned ref_epoch = 0;
   DevBuf<Stats> stats;
   DevBuf<M3P2ICommandInfo> info;
   bool have_noise = false, have_row0 = false, have_filt = false, have_evr = false;
@@ -254,6 +257,21 @@ int materialize(H* h) {
   return 0;
 }
 
+// lanes per sample of the rollout kernel: the lane-cooperative team kernel shortens the per-sample serial chain and
+// wins while the GPU is not full (16 * K threads <= ~1 resident wave); beyond that the redundant work of a team
+// costs more than it hides. cfg.lanes_per_sample: 0 = choose, 1 = thread per sample, 16 = team.
+int rollout_lanes(const H* h) {
+  if (h->cfg.env_type != M3P2I_ENV_PANDA) return 1;
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("M3P2I_LANES");
+    forced = e ? atoi(e) : 0;
+  }
+  int want = forced ? forced : h->cfg.lanes_per_sample;
+  if (want == 1 || want == 16) return want;
+  return h->cfg.num_samples <= 16384 ? 16 : 1;
+}
+
 RolloutCfg make_rcfg(const H* h) {
   const M3P2IConfig& c = h->cfg;
   RolloutCfg r;
@@ -262,6 +280,7 @@ RolloutCfg make_rcfg(const H* h) {
   r.multi_modal = c.multi_modal; r.null_action = c.sample_null_action; r.noise_mode = c.noise_mode;
   r.substeps = c.substeps; r.passes = c.solver_passes; r.task = h->task; r.gripper = h->gripper;
   r.env_live = h->env_live ? 1 : 0; r.store_env = h->env_alloc ? 1 : 0; r.open_loop = 0;
+  r.lanes = rollout_lanes(h);
   r.dt = c.dt; r.gamma = c.gamma; r.u_scale = c.u_scale; r.kp_suction = c.kp_suction;
   r.pre_height_diff = c.pre_height_diff; r.tilt_cos = c.tilt_cos_theta;
   memcpy(r.u_min, c.u_min, sizeof(r.u_min)); memcpy(r.u_max, c.u_max, sizeof(r.u_max));
@@ -278,6 +297,7 @@ RolloutBufs make_rbufs(const H* h) {
   b.seq = h->seq.p; b.actions_in = nullptr; b.base = h->base.p; b.env = h->env.p; b.vel_target = h->vel_target.p;
   b.actions = h->actions.p; b.states = h->states.p; b.cost_h = h->cost_h.p; b.J = h->J.p; b.cost_sum = h->cost_sum.p;
   b.refs = nullptr;
+  b.ref_flags = h->ref_flags.p;
   return b;
 }
 
@@ -332,6 +352,8 @@ int run_rollout(H* h, int* launches, const float* actions_in_dev) {
     if (!c.open_loop && !c.multi_modal && !own0 && c.noise_mode == M3P2I_NOISE_TABLE && !h->have_row0)
       return fail(M3P2I_ERR_STATE, "table noise: shards that do not own sample 0 need m3p2i_set_noise_row0");
     b.refs = h->refs.p;
+    h->ref_epoch += 64;   // > max horizon: flags of this launch run from epoch+1 to epoch+T
+    c.epoch = h->ref_epoch;
   }
   launch_rollout(h->cfg.env_type, c, &h->pp, &h->qp, b, refs, h->stream, launches);
   CK(cudaGetLastError());
@@ -501,6 +523,7 @@ int m3p2i_create(const M3P2IConfig* cfg, int device, m3p2i_handle* out) {
   if (e == cudaSuccess) e = h->cost_total.alloc(K);
   if (e == cudaSuccess) e = h->result.alloc(2 * TN);
   if (e == cudaSuccess) e = h->refs.alloc(T);
+  if (e == cudaSuccess) e = h->ref_flags.alloc(2);
   if (e == cudaSuccess) e = h->stats.alloc(1);
   if (e == cudaSuccess) e = h->info.alloc(1);
   if (e == cudaSuccess) {
@@ -529,7 +552,7 @@ void m3p2i_destroy(m3p2i_handle h) {
   h->env.release(); h->vel_target.release(); h->actions.release(); h->cost_h.release(); h->J.release();
   h->cost_sum.release(); h->J_global.release(); h->weights.release(); h->partials.release(); h->filt.release();
   h->cost_total.release(); h->result.release(); h->links.release(); h->scratch.release(); h->states.release();
-  h->refs.release(); h->stats.release(); h->info.release();
+  h->refs.release(); h->ref_flags.release(); h->stats.release(); h->info.release();
   if (h->pin) cudaFreeHost(h->pin);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);

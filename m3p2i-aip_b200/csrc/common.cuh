@@ -56,6 +56,8 @@ struct RolloutCfg {
   int env_live;     // 1: start from the persistent env buffer, 0: from the broadcast base state
   int store_env;    // write the end state (and last velocity target) back to the env buffer
   int open_loop;    // actions are supplied (m3p2i_rollout_actions) instead of sampled
+  unsigned epoch;   // ref_flags reach epoch + t + 1 when step t of this launch has been published
+  int lanes;        // lanes per sample: 1 = one thread per sample, 16 = lane-cooperative team (panda_env)
   float dt, gamma, u_scale, kp_suction, pre_height_diff, tilt_cos;
   float u_min[kMaxNu], u_max[kMaxNu], sigma[kMaxNu];
   float goal[8];
@@ -81,7 +83,8 @@ struct RolloutBufs {
   float* cost_h;           // [T][K]
   float* J;                // [K]  discounted cost
   float* cost_sum;         // [K]  undiscounted sum
-  PandaRef* refs;          // [T]
+  PandaRef* refs;          // [T] rows 0 / Kg/2 of the batch, published step by step by the producer CTA
+  unsigned* ref_flags;     // [2] progress counters of the two producers (cube position, cube axis)
 };
 
 // ------------------------------------------------------------------ small math

@@ -4,6 +4,7 @@
 
 #include "kernels.cuh"
 #include "panda_env.cuh"
+#include "panda_team.cuh"
 #include "point_env.cuh"
 
 namespace m3 {
@@ -35,6 +36,33 @@ DEV float env_cost(PandaEnv& e, const PandaParams& P, const RolloutCfg& c, int k
 // Perturbed action of GLOBAL sample kg at step t (mppi.py:392-416). `kl` is its row in this shard's tables, or -1.
 // The planner sequences are read time-shifted by one step (MPPI._shift_action, mppi.py:266-273): the shift itself
 // is applied to the stored mean in k_finish.
+// mean + sigma * delta, clamp, mode / gripper / null-action overrides for given unit noise `delta` (mppi.py:392-416)
+template <int NU>
+DEV void perturb_action(const RolloutCfg& c, const RolloutBufs& b, int kg, int t, const float* delta_in, float* u) {
+  const int TN = c.T * NU, half = c.Kg / 2;
+  const int ts = min(t + 1, c.T - 1);
+  const float* mean = b.seq + (c.multi_modal ? (kg < half ? SEQ_MEAN1 : SEQ_MEAN2) : SEQ_MEAN) * TN + ts * NU;
+#pragma unroll
+  for (int d = 0; d < NU; ++d) {
+    const float delta = kg == c.Kg - 1 ? 0.0f : delta_in[d];
+    float v = mean[d] + delta * c.sigma[d];
+    v = fmaxf(fminf(v, c.u_max[d]), c.u_min[d]);
+    if (c.multi_modal) {
+      if (kg == 0) v = b.seq[SEQ_BEST1 * TN + ts * NU + d];
+      if (kg == half) v = b.seq[SEQ_BEST2 * TN + ts * NU + d];
+    }
+    if (NU == 9 && d >= 7) {
+      if (c.gripper == M3P2I_GRIPPER_OPEN) v = 1.5f;
+      else if (c.gripper == M3P2I_GRIPPER_CLOSE) v = -1.5f;
+    }
+    u[d] = c.u_scale * v;
+  }
+  if (c.null_action && kg == c.Kg - 1) {
+#pragma unroll
+    for (int d = 0; d < NU; ++d) u[d] = 0.0f;
+  }
+}
+
 template <int NU>
 DEV void sample_action(const RolloutCfg& c, const RolloutBufs& b, int kg, int kl, int t, float* u) {
   const int K = c.K, TN = c.T * NU, half = c.Kg / 2;
@@ -76,15 +104,64 @@ DEV void sample_action(const RolloutCfg& c, const RolloutBufs& b, int kg, int kl
   }
 }
 
+// ------------------------------------------------------------------ rows 0 and Kg/2 of the batch (panda reach)
+// Every sample's reach cost reads, after each step, the cube position of sample 0 (cost_functions.py:98,102-103)
+// and the cube axis picked from the first row of the second half (skill_utils.py:275-279 on [half_samples:],
+// cost_functions.py:151-152). CTA 0 of the rollout grid is a PRODUCER: it replays those two rows (a shard that does
+// not own them reconstructs them from the planner state) and publishes refs[t] step by step; all other CTAs are
+// consumers that wait for step t before evaluating their cost. CTA 0 is dispatched first, so the producer is
+// resident before any consumer can spin, whatever the grid size.
+DEV void ref_publish(const RolloutBufs& b, int which, int t, unsigned epoch, const Cube& cubeA, bool with_axis) {
+  volatile PandaRef* r = b.refs + t;
+  if (which == 0) { r->cube0[0] = cubeA.p.x; r->cube0[1] = cubeA.p.y; r->cube0[2] = cubeA.p.z; }
+  if (which == 1 || with_axis) r->sel_axis = sel_axis_of(cubeA);
+  __threadfence();
+  *(volatile unsigned*)(b.ref_flags + which) = epoch + (unsigned)t + 1u;
+}
+DEV PandaRef ref_wait(const RolloutBufs& b, int t, unsigned epoch, bool two) {
+  const unsigned target = epoch + (unsigned)t + 1u;
+  while ((int)(*(volatile unsigned*)(b.ref_flags + 0) - target) < 0) {}
+  if (two) while ((int)(*(volatile unsigned*)(b.ref_flags + 1) - target) < 0) {}
+  __threadfence();
+  const volatile PandaRef* r = b.refs + t;
+  PandaRef out;
+  out.cube0[0] = r->cube0[0]; out.cube0[1] = r->cube0[1]; out.cube0[2] = r->cube0[2]; out.sel_axis = r->sel_axis;
+  return out;
+}
+
 // ------------------------------------------------------------------ fused rollout
 // noise -> perturbation -> clamp -> T x (dynamics step, task cost, discounted accumulate) with per-step stores of
 // the action planes, the float4 state row and the cost (mppi.py:275-332 with reactive_tamp.py:63-73 inlined).
+// producer for the thread-per-sample kernel: thread 0 replays global row 0, thread 1 global row Kg/2
+template <typename Params>
+DEV void produce_refs(const RolloutCfg&, const Params&, const RolloutBufs&, int) {}
+template <>
+DEV void produce_refs<PandaParams>(const RolloutCfg& c, const PandaParams& P, const RolloutBufs& b, int which) {
+  if (which > (c.multi_modal ? 1 : 0)) return;
+  const int kg = which == 0 ? 0 : c.Kg / 2;
+  const int kl = (kg >= c.offset && kg < c.offset + c.K) ? kg - c.offset : -1;
+  PandaEnv e;
+  if (c.env_live && kl >= 0) e.load(b.env, c.K, kl);
+  else e.load(b.base, 1, 0);
+  float u[9];
+  for (int t = 0; t < c.T; ++t) {
+    sample_action<9>(c, b, kg, kl, t, u);
+    panda_step(e, P, u, c.dt, c.substeps, c.passes);
+    ref_publish(b, which, t, c.epoch, e.cube[0], !c.multi_modal);
+  }
+}
+
 template <int ENV>
 __global__ void __launch_bounds__(kRolloutBlock)
 k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename EnvOf<ENV>::Params P, const RolloutBufs b) {
   using Env = typename EnvOf<ENV>::Env;
   constexpr int NU = EnvOf<ENV>::NU;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool use_refs = ENV == M3P2I_ENV_PANDA && b.refs != nullptr;
+  if (use_refs && blockIdx.x == 0) {
+    if (ENV == M3P2I_ENV_PANDA) produce_refs(c, P, b, threadIdx.x);
+    return;
+  }
+  const int k = (blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x + threadIdx.x;
   if (k >= c.K) return;
   const int K = c.K, kg = c.offset + k;
   Env e;
@@ -95,7 +172,9 @@ k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename
   for (int t = 0; t < c.T; ++t) {
     sample_action<NU>(c, b, kg, k, t, u);
     env_step(e, P, u, c);
-    const float cost = env_cost(e, P, c, kg, (ENV == M3P2I_ENV_PANDA && b.refs) ? &b.refs[t] : nullptr);
+    PandaRef ref;
+    if (use_refs) ref = ref_wait(b, t, c.epoch, c.multi_modal != 0);
+    const float cost = env_cost(e, P, c, kg, use_refs ? &ref : nullptr);
     run += cost;
     J += g * cost;
     g *= c.gamma;
@@ -113,26 +192,67 @@ k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename
   }
 }
 
-// Rows 0 and Kg/2 of the GLOBAL batch, replayed by two threads so that every sample's reach cost can read the cube
-// position of sample 0 (cost_functions.py:98,102-103) and the cube axis picked from the first row of the second
-// half (skill_utils.py:275-279 on [half_samples:], cost_functions.py:151-152).
-__global__ void k_refs(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
-  const int which = threadIdx.x;
-  if (which > (c.multi_modal ? 1 : 0)) return;
-  const int kg = which == 0 ? 0 : c.Kg / 2;
-  const int kl = (kg >= c.offset && kg < c.offset + c.K) ? kg - c.offset : -1;
-  PandaEnv e;
-  if (c.env_live && kl >= 0) e.load(b.env, c.K, kl);
-  else e.load(b.base, 1, 0);
-  float u[9];
-  for (int t = 0; t < c.T; ++t) {
-    sample_action<9>(c, b, kg, kl, t, u);
-    panda_step(e, P, u, c.dt, c.substeps, c.passes);
-    if (which == 0) {
-      b.refs[t].cube0[0] = e.cube[0].p.x; b.refs[t].cube0[1] = e.cube[0].p.y; b.refs[t].cube0[2] = e.cube[0].p.z;
-      if (!c.multi_modal) b.refs[t].sel_axis = sel_axis_of(e.cube[0]);
+// Lane-cooperative variant for panda_env: 16 lanes per sample (panda_team.cuh), two samples per warp.
+__global__ void __launch_bounds__(kRolloutBlock, 14)
+k_rollout_team(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
+  constexpr int NU = 9;
+  const TeamLane t = team_lane();
+  const bool use_refs = b.refs != nullptr;
+  const bool producer = use_refs && blockIdx.x == 0;
+  const int which = t.lane >> 4;   // producer CTA: team 0 replays global row 0, team 1 global row Kg/2
+  const int kraw = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x + threadIdx.x) / kTeam;
+  const bool valid = !producer && kraw < c.K;
+  const int K = c.K;
+  int k = kraw < c.K ? kraw : c.K - 1;   // idle teams shadow the last sample so that every shuffle has 32 lanes
+  int kg = c.offset + k;
+  if (producer) {
+    kg = (which == 1 && c.multi_modal) ? c.Kg / 2 : 0;
+    k = (kg >= c.offset && kg < c.offset + c.K) ? kg - c.offset : -1;
+  }
+  const bool writer = valid && (t.lane & (kTeam - 1)) == 0;
+  TeamEnv e;
+  if (c.env_live && k >= 0) e.load(b.env, K, k, t.g);
+  else e.load(b.base, 1, 0, t.g);
+  float run = 0.0f, J = 0.0f, g = 1.0f;
+  float u[NU];
+  for (int step = 0; step < c.T; ++step) {
+    if (c.noise_mode == M3P2I_NOISE_PHILOX && !c.open_loop) {
+      // the three Philox blocks (dims 0-3, 4-7, 8) are drawn by lanes 0..2 of the team and broadcast
+      float z[4];
+      normal4(c.seed_lo, c.seed_hi, (uint32_t)kg, (uint32_t)step, (uint32_t)min(t.lane & 15, 2), z);
+      float zz[NU];
+#pragma unroll
+      for (int d = 0; d < NU; ++d) zz[d] = __shfl_sync(kFull, z[d & 3], t.team_base + (d >> 2));
+      perturb_action<NU>(c, b, kg, step, zz, u);
     } else {
-      b.refs[t].sel_axis = sel_axis_of(e.cube[0]);
+      sample_action<NU>(c, b, kg, k, step, u);
+    }
+    team_panda_step(e, P, u, c.dt, c.substeps, c.passes, t);
+    PandaRef ref;
+    if (producer) {
+      // group 0 of each team holds cubeA; its first lane publishes (team 1 only when the batch is multi-modal)
+      if ((t.lane & 15) == 0 && (which == 0 || c.multi_modal)) ref_publish(b, which, step, c.epoch, e.cu, !c.multi_modal);
+      continue;
+    }
+    if (use_refs) ref = ref_wait(b, step, c.epoch, c.multi_modal != 0);
+    const float cost = team_panda_cost(e, P, c, kg, use_refs ? &ref : nullptr, t);
+    run += cost;
+    J += g * cost;
+    g *= c.gamma;
+    if (writer) {
+#pragma unroll
+      for (int d = 0; d < NU; ++d) b.actions[(size_t)(step * NU + d) * K + k] = u[d];
+      b.states[(size_t)step * K + k] = e.state_row();
+      b.cost_h[(size_t)step * K + k] = cost;
+    }
+  }
+  if (writer) { b.J[k] = J; b.cost_sum[k] = run; }
+  if (producer) return;
+  if (c.store_env && valid) {
+    e.store(b.env, K, k, t);
+    if (writer) {
+#pragma unroll
+      for (int d = 0; d < NU; ++d) b.vel_target[(size_t)d * K + k] = u[d];
     }
   }
 }
@@ -153,18 +273,17 @@ static int rollout_block(int K) {
 void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp,
                     const RolloutBufs& b, bool need_refs, cudaStream_t st, int* launches) {
   const int block = rollout_block(c.K);
-  const int grid = (c.K + block - 1) / block;
+  const int extra = need_refs ? 1 : 0;   // CTA 0 = producer of the batch rows every reach cost reads
+  const int grid = (c.K + block - 1) / block + extra;
   if (env_type == M3P2I_ENV_POINT) {
     k_rollout<M3P2I_ENV_POINT><<<grid, block, 0, st>>>(c, *pp, b);
-    ++*launches;
+  } else if (c.lanes == kTeam) {
+    const int teams_per_block = kRolloutBlock / kTeam;
+    k_rollout_team<<<(c.K + teams_per_block - 1) / teams_per_block + extra, kRolloutBlock, 0, st>>>(c, *qp, b);
   } else {
-    if (need_refs) {
-      k_refs<<<1, 32, 0, st>>>(c, *qp, b);
-      ++*launches;
-    }
     k_rollout<M3P2I_ENV_PANDA><<<grid, block, 0, st>>>(c, *qp, b);
-    ++*launches;
   }
+  ++*launches;
 }
 
 // ------------------------------------------------------------------ block reductions (fixed order => reproducible)

@@ -112,6 +112,9 @@ class MPPI():
             self.backend = sim.attach_planner(cfg, noise_mode=noise_mode, seed=self.seed_val)
         else:
             self._sim, self._objective = None, None
+            if isinstance(sim, IsaacGymWrapper) and sim.num_envs == self.K:
+                # the callbacks will step this sim themselves; give its cost / suction kernels the full configuration
+                sim.attach_planner(cfg, noise_mode=A.NOISE_TABLE, seed=self.seed_val)
             scene = S.build_point_scene() if self.env_type == "point_env" else S.build_panda_scene()
             self.backend = native.NativePlanner(S.build_config(cfg, noise_mode=noise_mode, seed=self.seed_val), scene)
             # the softmin/update kernels need no scene state, but the handle wants one

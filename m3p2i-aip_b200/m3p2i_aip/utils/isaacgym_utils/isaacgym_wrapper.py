@@ -105,6 +105,7 @@ class IsaacGymWrapper:
                                   and np.array_equal(root, np.broadcast_to(root[0], root.shape))):
             b.set_state(dof[0], root[0])
         else:
+            b.set_state(dof[0], root[0])   # fixed actors / floating plate pose
             b.sim_write(dof, root)
         self._push_pending = False
 

@@ -267,7 +267,7 @@ def build_config(cfg, num_samples_local=None, sample_offset=0, noise_mode=A.NOIS
     ig = getattr(cfg, "isaacgym", None)
     c.substeps = int(getattr(ig, "substeps", 2)) if ig is not None else 2
     c.solver_passes = 2
-    c.lanes_per_sample = 1
+    c.lanes_per_sample = int(getattr(m, "lanes_per_sample", 0))  # 0 = let the library choose
     c.dt = float(getattr(ig, "dt", 0.05 if c.env_type == A.ENV_POINT else 0.01)) if ig is not None else \
         (0.05 if c.env_type == A.ENV_POINT else 0.01)
     c.gamma = float(getattr(m, "rollout_var_discount", 0.95))

@@ -209,3 +209,41 @@ def test_panda_fk_known_answers():
     ref = np.array([-0.92185, -0.38184, 0.06116, 0.02533])
     assert min(np.abs(q - ref).max(), np.abs(q + ref).max()) < 2e-5
     n.close()
+
+
+@pytest.mark.parametrize("task,mm,shelf", [("pick", False, False), ("reach", True, True), ("reach", False, False)])
+def test_team_and_thread_kernels_agree(task, mm, shelf):
+    """The lane-cooperative (16 lanes per sample) and the thread-per-sample rollout kernels apply the same impulses
+    in the same order; only the summation order of the reported contact forces differs."""
+    O.set_threads(8)
+    case = ("x", "panda_env", task, None, 512, 16, mm, shelf, None)
+    res = {}
+    for lanes in (1, 16):
+        cfg, o, n = _setup(case, A.NOISE_PHILOX)
+        n.close()
+        cfg.mppi.lanes_per_sample = lanes
+        n = make_backend(native.NativePlanner, cfg, noise_mode=A.NOISE_PHILOX, seed=7)
+        actors = S.default_actors("panda_env")
+        dof, root = S.initial_dof_state(actors).copy(), S.initial_root_state(actors, shelf).copy()
+        # start with the gripper around cubeA so that finger / cube contacts are exercised
+        if task == "pick":
+            dof[0::2] = [0.0, 0.55, 0.0, -1.95, 0.0, 2.5, 0.785, 0.03, 0.03]
+        cb = root[S.actor_index(actors, "cubeB")]
+        goal = np.concatenate([cb[:3] + np.array([0, 0, 0.055], np.float32), cb[3:7]]) if task == "pick" else np.zeros(7)
+        for b in (o, n):
+            b.set_state(dof, root)
+            b.set_objective(task, goal, {"pick": "close", "reach": "open"}[task])
+        outs = []
+        for i in range(3):
+            a_n, c_n, _ = n.command()
+            outs.append((a_n.copy(), c_n.copy(), n.read_buffer(A.BUF_STATES), n.read_buffer(A.BUF_COST_HORIZON)))
+            if lanes == 16:
+                a_o, c_o, _ = o.command()
+                assert_close(c_n, c_o, RTOL, 5e-3, f"team vs oracle cost_total [{i}]", 0.01)
+                assert_close(a_n, a_o, 1e-2, 1e-2, f"team vs oracle action [{i}]")
+        res[lanes] = outs
+        o.close()
+        n.close()
+    for i in range(3):
+        for j, what in enumerate(("action", "cost_total", "states", "cost_horizon")):
+            assert_close(res[16][i][j], res[1][i][j], 1e-4, 1e-4, f"team vs thread {what} [{i}]", 0.005)
