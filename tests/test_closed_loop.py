@@ -1,0 +1,139 @@
+"""Closed-loop behaviour: the planner drives a K=1 "real world" env of the same integrator, exactly
+like scripts/sim.py + scripts/reactive_tamp.py do over zerorpc, and must solve the task. This is the only
+behaviour-level ground truth available (PhysX itself cannot be run). CPU variants use the oracle backend."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_py as O
+from m3p2i_aip.planners.motion_planner import m3p2i
+from m3p2i_aip.planners.motion_planner.cost_functions import Objective
+from m3p2i_aip.utils.isaacgym_utils import isaacgym_wrapper as wrapper
+from m3p2i_aip.utils.skill_utils import check_and_apply_suction
+from m3p2i_b200 import scene as S
+
+
+class Planner:
+    """REACTIVE_TAMP (scripts/reactive_tamp.py:21-87) with a fixed task instead of the task planner."""
+
+    def __init__(self, cfg, factory):
+        self.sim = wrapper.IsaacGymWrapper(cfg.isaacgym, cfg.env_type, num_envs=cfg.mppi.num_samples, device="cpu",
+                                           cube_on_shelf=cfg.cube_on_shelf, backend_factory=factory)
+        self.objective = Objective(cfg)
+        self.mp = m3p2i.M3P2I(cfg, dynamics=self.dynamics, running_cost=self.running_cost)
+
+    def dynamics(self, _, u, t=None):
+        raise AssertionError("the fused path must not call back into Python")
+
+    def running_cost(self, _):
+        raise AssertionError("the fused path must not call back into Python")
+
+    def run_tamp(self, dof, root, task, goal):
+        self.sim._dof_state[:] = dof
+        self.sim._root_state[:] = root
+        self.sim.set_dof_state_tensor(self.sim._dof_state)
+        self.sim.set_actor_root_state_tensor(self.sim._root_state)
+        self.mp.update_gripper_command(task)
+        self.objective.update_objective(task, goal)
+        return self.mp.command(self.sim._dof_state[0])[0]
+
+
+def run_episode(env, task, goal, K, T, ticks, factory, sampling, mm=False, robot=None, done=None):
+    cfg = S.make_cfg(env, task, goal, K, T, multi_modal=mm)
+    cfg.mppi.sampling_method = sampling
+    if sampling == "halton":
+        pass  # the once-sampled Halton-spline table (host, scipy)
+    planner = Planner(cfg, factory)
+    real = wrapper.IsaacGymWrapper(cfg.isaacgym, env, num_envs=1, device="cpu", backend_factory=factory)
+    if robot is not None:
+        real._dof_state[0, 0], real._dof_state[0, 2] = robot
+        real.set_dof_state_tensor(real._dof_state)
+    g = torch.tensor(goal, dtype=torch.float32)
+    trace = []
+    for i in range(ticks):
+        action = planner.run_tamp(real._dof_state.clone(), real._root_state.clone(), task, g)
+        real.set_dof_velocity_target_tensor(action.view(1, -1))
+        cfg.suction_active = planner.mp.get_pull_preference()   # scripts/sim.py:47-50
+        check_and_apply_suction(cfg, real, action)
+        real.step()
+        trace.append(real._dof_state[0].clone())
+        if done is not None and done(real):
+            break
+    return real, planner, i + 1
+
+
+def _box_dist(real, goal):
+    return float(torch.linalg.norm(real.get_actor_position_by_name("box")[0, :2] - torch.tensor(goal)))
+
+
+def test_navigation_reaches_goal_cpu():
+    """PLANNER_SIMPLE.check_task_success: |robot - goal| < 0.1 (task_planner.py:18,30-32)."""
+    goal = [1.5, -1.0]
+    done = lambda r: float(torch.linalg.norm(r.robot_pos[0] - torch.tensor(goal))) < 0.1
+    real, _, n = run_episode("point_env", "navigation", goal, 64, 12, 120, O.Oracle.for_sim, "halton", done=done)
+    assert done(real), f"robot at {real.robot_pos[0].tolist()} after {n} ticks"
+
+
+def test_push_moves_block_towards_goal_cpu():
+    goal = [0.0, 3.2]
+    real, _, n = run_episode("point_env", "push", goal, 96, 16, 150, O.Oracle.for_sim, "halton", robot=[0.0, 1.0],
+                             done=lambda r: _box_dist(r, goal) < 0.15)
+    assert _box_dist(real, goal) < 0.6, f"block at {real.get_actor_position_by_name('box')[0, :2].tolist()} after {n} ticks"
+
+
+def test_pull_brings_block_to_goal_cpu():
+    """`task=pull goal=[0,0]`: suction in the rollouts (cost_functions.py:71-76) and in the real env (sim.py:47-50)."""
+    goal = [0.0, 0.0]
+    real, _, n = run_episode("point_env", "pull", goal, 128, 20, 250, O.Oracle.for_sim, "halton",
+                             done=lambda r: _box_dist(r, goal) < 0.1)
+    assert _box_dist(real, goal) < 0.1, f"block {_box_dist(real, goal):.2f} from the goal after {n} ticks"
+
+
+@pytest.mark.gpu
+def test_navigation_avoids_obstacle_gpu():
+    """Goal behind the dynamic obstacle at (-2, 2): reach it without ever touching the obstacle."""
+    goal = [-3.0, 3.0]
+    touched = []
+
+    def done(r):
+        touched.append(float(r.get_actor_contact_forces_by_name("dyn-obs", "box")[0, :2].abs().sum()))
+        return float(torch.linalg.norm(r.robot_pos[0] - torch.tensor(goal))) < 0.1
+    real, _, n = run_episode("point_env", "navigation", goal, 512, 15, 200, None, "philox", done=done)
+    assert float(torch.linalg.norm(real.robot_pos[0] - torch.tensor(goal))) < 0.1, real.robot_pos[0].tolist()
+    assert max(touched) < 0.1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task,mm,goal", [("push", False, [-1.0, -1.0]), ("pull", False, [0.0, 0.0]),
+                                          ("push_pull", True, [-2.5, -2.5])])
+def test_block_tasks_gpu(task, mm, goal):
+    """README commands `task=push goal=[-1,-1]`, `task=pull goal=[0,0]`, `task=push_pull multi_modal=True`:
+    success = block within dist_threshold of the goal (task_planner.py:33-38); here: large progress in 400 ticks."""
+    d0 = float(np.linalg.norm(np.array([0.0, 2.0]) - np.array(goal)))
+    real, planner, n = run_episode("point_env", task, goal, 1024, 20, 400, None, "philox", mm=mm,
+                                   done=lambda r: _box_dist(r, goal) < 0.1)
+    d = _box_dist(real, goal)
+    assert d < 0.35 * d0, f"{task}: block still {d:.2f} from the goal (started {d0:.2f}) after {n} ticks"
+
+
+@pytest.mark.gpu
+def test_panda_reach_gpu():
+    """reach: the gripper ends above cubeA within pre_height_diff + 0.005 (PLANNER_AIF_PANDA.get_obs threshold,
+    task_planner.py:57,70-73), fingers pointing down."""
+    cfg = S.make_cfg("panda_env", "reach", None, 1024, 16)
+    cfg.mppi.sampling_method = "philox"
+    planner = Planner(cfg, None)
+    real = wrapper.IsaacGymWrapper(cfg.isaacgym, "panda_env", num_envs=1, device="cpu")
+    goal = torch.zeros(7)
+    best = 1e9
+    for i in range(300):
+        action = planner.run_tamp(real._dof_state.clone(), real._root_state.clone(), "reach", goal)
+        real.set_dof_velocity_target_tensor(action.view(1, -1))
+        real.step()
+        ee = 0.5 * (real.get_actor_link_by_name("panda", "panda_leftfinger")[0, :3]
+                    + real.get_actor_link_by_name("panda", "panda_rightfinger")[0, :3])
+        cube = real.get_actor_link_by_name("cubeA", "box")[0, :3]
+        best = min(best, float(torch.linalg.norm(ee - cube)))
+        if best < cfg.pre_height_diff + 0.005:
+            break
+    assert best < cfg.pre_height_diff + 0.02, f"closest approach {best:.3f} m after {i + 1} ticks"
