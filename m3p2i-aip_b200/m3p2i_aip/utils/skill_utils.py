@@ -57,3 +57,39 @@ def check_and_apply_suction(cfg, sim, action, verbose=False):
     if verbose:
         print("suction!!!" if applied else "no suction...")
     return applied
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Quaternion orientation costs (skill_utils.py:140-180, 224-289). Inside the rollout they are evaluated by the CUDA
+# kernels (panda_env.cuh); these host versions serve callers outside the hot path, e.g. the reference's task planner
+# (task_planner.py:61), on small tensors.
+def quaternion_rotation_matrix(Q):
+    """[N,4] quaternions (x, y, z, w) -> [N,3,3] rotation matrices, same element formulas as the reference."""
+    x, y, z, w = Q[:, 0], Q[:, 1], Q[:, 2], Q[:, 3]
+    rows = (2 * (w * w + x * x) - 1, 2 * (x * y - w * z), 2 * (x * z + w * y),
+            2 * (x * y + w * z), 2 * (w * w + y * y) - 1, 2 * (y * z - w * x),
+            2 * (x * z - w * y), 2 * (y * z + w * x), 2 * (w * w + z * z) - 1)
+    return torch.stack(rows, dim=1).reshape(Q.shape[0], 3, 3)
+
+
+def _min_axis_cost(axis, R):
+    """min over the three columns c of R of 1 - |<axis, c>|, per batch row."""
+    return (1 - torch.abs(torch.einsum("ni,nij->nj", axis, R))).min(dim=1)[0]
+
+
+def get_general_ori_cube2goal(cube_quaternion, goal_quatenion):
+    """Alignment of the goal's x and y axes with any cube axis (invariant to flipped cubes)."""
+    C, G = quaternion_rotation_matrix(cube_quaternion), quaternion_rotation_matrix(goal_quatenion)
+    return _min_axis_cost(G[:, :, 0], C) + _min_axis_cost(G[:, :, 1], C)
+
+
+def get_general_ori_ee2cube(ee_quaternion, cube_quaternion, tilt_value=0):
+    """End-effector z axis perpendicular to a cube face (or at `tilt_value` to the cube axis closest to world x, taken
+    from the FIRST row, skill_utils.py:275-279) plus y-axis alignment."""
+    E, C = quaternion_rotation_matrix(ee_quaternion), quaternion_rotation_matrix(cube_quaternion)
+    if tilt_value == 0:
+        cost_z = _min_axis_cost(E[:, :, 2], C)
+    else:
+        sel = int(torch.argmax(torch.abs(C[0, 0, :])))
+        cost_z = torch.abs(tilt_value - torch.sum(E[:, :, 2] * C[:, :, sel], dim=1))
+    return cost_z + _min_axis_cost(E[:, :, 1], C)
