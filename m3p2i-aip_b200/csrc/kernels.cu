@@ -4,7 +4,6 @@
 
 #include "kernels.cuh"
 #include "panda_env.cuh"
-#include "panda_team.cuh"
 #include "point_env.cuh"
 
 namespace m3 {
@@ -192,69 +191,29 @@ k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename
   }
 }
 
+}  // namespace m3
+
+#include "panda_team.cuh"   // needs sample_action / perturb_action / ref_publish / ref_wait from above
+
+namespace m3 {
+
 // Lane-cooperative variant for panda_env: 16 lanes per sample (panda_team.cuh), two samples per warp.
+// CTA 0 is the producer of the batch rows read by the reach cost when b.refs is set.
 __global__ void __launch_bounds__(kRolloutBlock, 14)
 k_rollout_team(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
-  constexpr int NU = 9;
   const TeamLane t = team_lane();
   const bool use_refs = b.refs != nullptr;
   const bool producer = use_refs && blockIdx.x == 0;
   const int which = t.lane >> 4;   // producer CTA: team 0 replays global row 0, team 1 global row Kg/2
   const int kraw = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x + threadIdx.x) / kTeam;
   const bool valid = !producer && kraw < c.K;
-  const int K = c.K;
   int k = kraw < c.K ? kraw : c.K - 1;   // idle teams shadow the last sample so that every shuffle has 32 lanes
   int kg = c.offset + k;
   if (producer) {
     kg = (which == 1 && c.multi_modal) ? c.Kg / 2 : 0;
     k = (kg >= c.offset && kg < c.offset + c.K) ? kg - c.offset : -1;
   }
-  const bool writer = valid && (t.lane & (kTeam - 1)) == 0;
-  TeamEnv e;
-  if (c.env_live && k >= 0) e.load(b.env, K, k, t.g);
-  else e.load(b.base, 1, 0, t.g);
-  float run = 0.0f, J = 0.0f, g = 1.0f;
-  float u[NU];
-  for (int step = 0; step < c.T; ++step) {
-    if (c.noise_mode == M3P2I_NOISE_PHILOX && !c.open_loop) {
-      // the three Philox blocks (dims 0-3, 4-7, 8) are drawn by lanes 0..2 of the team and broadcast
-      float z[4];
-      normal4(c.seed_lo, c.seed_hi, (uint32_t)kg, (uint32_t)step, (uint32_t)min(t.lane & 15, 2), z);
-      float zz[NU];
-#pragma unroll
-      for (int d = 0; d < NU; ++d) zz[d] = __shfl_sync(kFull, z[d & 3], t.team_base + (d >> 2));
-      perturb_action<NU>(c, b, kg, step, zz, u);
-    } else {
-      sample_action<NU>(c, b, kg, k, step, u);
-    }
-    team_panda_step(e, P, u, c.dt, c.substeps, c.passes, t);
-    PandaRef ref;
-    if (producer) {
-      // group 0 of each team holds cubeA; its first lane publishes (team 1 only when the batch is multi-modal)
-      if ((t.lane & 15) == 0 && (which == 0 || c.multi_modal)) ref_publish(b, which, step, c.epoch, e.cu, !c.multi_modal);
-      continue;
-    }
-    if (use_refs) ref = ref_wait(b, step, c.epoch, c.multi_modal != 0);
-    const float cost = team_panda_cost(e, P, c, kg, use_refs ? &ref : nullptr, t);
-    run += cost;
-    J += g * cost;
-    g *= c.gamma;
-    if (writer) {
-#pragma unroll
-      for (int d = 0; d < NU; ++d) b.actions[(size_t)(step * NU + d) * K + k] = u[d];
-      b.states[(size_t)step * K + k] = e.state_row();
-      b.cost_h[(size_t)step * K + k] = cost;
-    }
-  }
-  if (writer) { b.J[k] = J; b.cost_sum[k] = run; }
-  if (producer) return;
-  if (c.store_env && valid) {
-    e.store(b.env, K, k, t);
-    if (writer) {
-#pragma unroll
-      for (int d = 0; d < NU; ++d) b.vel_target[(size_t)d * K + k] = u[d];
-    }
-  }
+  team_rollout(c, P, b, t, k, kg, valid, producer, which);
 }
 
 // Threads per CTA of the rollout kernel. The kernel is latency-bound (one serial chain per sample), so small CTAs

@@ -241,6 +241,48 @@ DEV V3 solve_cube_static(V3& v, V3& w, float im, float ii, V3 x, V3 n, float dep
   return jn * n - jt * t;
 }
 
+// Kinematic link (prescribed twist lv, lw about lx; a finger adds one sliding DoF of inverse mass ims along `axis`
+// with speed `slide`) against a free cube. Unit normal n points from the cube to the link. Same equations as
+// solve_contact3 with the vanishing terms removed. Returns the impulse on the link.
+DEV V3 solve_link_cube(V3 lv, V3 lw, V3 lx, V3 axis, float& slide, float ims, V3& v, V3& w, float im, float ii, V3 x,
+                       V3 n, float depth, V3 c, float mu, float h, const PandaParams& P) {
+  const V3 rl = c - lx, rc = c - x;
+  const V3 vl0 = lv + cross(lw, rl);   // part of the link's point velocity that contacts cannot change
+  V3 rv = (vl0 + slide * axis) - (v + cross(w, rc));
+  float vn = dot(rv, n);
+  const V3 rcn = cross(rc, n);
+  const float an = dot(axis, n);
+  const float kn = ims * an * an + im + ii * dot(rcn, rcn);
+  if (kn <= 0.0f) return mk(0, 0, 0);
+  float target;
+  if (depth > 0.0f) {
+    const float pen = fmaxf(depth - P.slop, 0.0f);
+    target = fminf(P.baumgarte * pen / h, P.max_corr_vel);
+  } else {
+    target = depth / h;
+  }
+  const float jn = (target - vn) / kn;
+  if (jn <= 0.0f) return mk(0, 0, 0);
+  slide += ims * an * jn;
+  v = v - (jn * im) * n;
+  w = w - (jn * ii) * rcn;
+  rv = (vl0 + slide * axis) - (v + cross(w, rc));
+  vn = dot(rv, n);
+  V3 t = rv - vn * n;
+  const float vt = sqrtf(dot(t, t));
+  if (vt < 1e-9f) return jn * n;
+  t = (1.0f / vt) * t;
+  const V3 rct = cross(rc, t);
+  const float at = dot(axis, t);
+  const float kt = ims * at * at + im + ii * dot(rct, rct);
+  if (kt <= 0.0f) return jn * n;
+  const float jt = fminf(vt / kt, mu * jn);
+  slide -= ims * at * jt;
+  v = v + (jt * im) * t;
+  w = w + (jt * ii) * rct;
+  return jn * n - jt * t;
+}
+
 struct OBox3 {
   V3 c;
   M33 R;
@@ -306,6 +348,23 @@ DEV void box_vs_box3(Dyn3& A, const OBox3& ba, Dyn3& B, const OBox3& bb, float m
       if (!point_in_box(p, ba, P.contact_margin, n, depth)) continue;
       accB = accB - solve_contact3(A, B, -n, depth, p, mu, h, P);
     }
+  }
+}
+
+DEV void link_vs_cube(V3 lv, V3 lw, V3 lx, V3 axis, float& slide, float ims, const OBox3& lb, V3& v, V3& w, float im,
+                      float ii, V3 x, const OBox3& cb, float mu, float h, const PandaParams& P, V3& accC) {
+  if (!boxes_near(lb, cb, P.contact_margin)) return;
+  for (int i = 0; i < 8; ++i) {   // corners of the link in the cube, normal out of the cube
+    const V3 p = box_corner(lb, i);
+    V3 n; float depth;
+    if (!point_in_box(p, cb, P.contact_margin, n, depth)) continue;
+    accC = accC - solve_link_cube(lv, lw, lx, axis, slide, ims, v, w, im, ii, x, n, depth, p, mu, h, P);
+  }
+  for (int i = 0; i < 8; ++i) {   // corners of the cube in the link, normal out of the link
+    const V3 p = box_corner(cb, i);
+    V3 n; float depth;
+    if (!point_in_box(p, lb, P.contact_margin, n, depth)) continue;
+    accC = accC - solve_link_cube(lv, lw, lx, axis, slide, ims, v, w, im, ii, x, -n, depth, p, mu, h, P);
   }
 }
 
@@ -420,8 +479,10 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
         V3 sink = mk(0, 0, 0);
-        box_vs_box3<true>(L[f], lbox[f], C[0], cbox[0], 0.5f * (P.robot_mu + P.cube_mu[0]), h, P, sink);
-        box_vs_box3<true>(L[f], lbox[f], C[1], cbox[1], 0.5f * (P.robot_mu + P.cube_mu[1]), h, P, imp_cubeb);
+        link_vs_cube(L[f].v, L[f].w, L[f].x, L[f].axis, L[f].slide, L[f].ims, lbox[f], C[0].v, C[0].w, C[0].im, C[0].ii,
+                     C[0].x, cbox[0], 0.5f * (P.robot_mu + P.cube_mu[0]), h, P, sink);
+        link_vs_cube(L[f].v, L[f].w, L[f].x, L[f].axis, L[f].slide, L[f].ims, lbox[f], C[1].v, C[1].w, C[1].im, C[1].ii,
+                     C[1].x, cbox[1], 0.5f * (P.robot_mu + P.cube_mu[1]), h, P, imp_cubeb);
       }
     }
 #pragma unroll
@@ -495,14 +556,14 @@ DEV float panda_motion_cost(const PandaEnv& e) {
   return (fabsf(fx) + fabsf(fy)) > 0.1f ? 1000.0f : 0.0f;
 }
 
-DEV float panda_cost(const PandaEnv& e, const PandaParams& P, const RolloutCfg& c, int kg, const PandaRef& ref) {
+// task cost given the hand pose (cost_functions.py:91-136): cubeA pose, finger openings q7/q8, contact-force cost
+DEV float panda_cost_from_hand(const Hand& H, float q7, float q8, const Cube& cubeA, float motion_cost,
+                               const RolloutCfg& c, int kg, const PandaRef& ref) {
   const bool second = c.multi_modal && kg >= c.Kg / 2;
   switch (c.task) {
     case M3P2I_TASK_REACH: {
-      Hand H;
-      panda_hand(P, e.q, e.qd, false, H);
       // ee = mean of the two finger frames (cost_functions.py:92-94)
-      const V3 lf = H.p + mul(H.R, mk(0.0f, e.q[7], kFingerZ)), rf = H.p + mul(H.R, mk(0.0f, -e.q[8], kFingerZ));
+      const V3 lf = H.p + mul(H.R, mk(0.0f, q7, kFingerZ)), rf = H.p + mul(H.R, mk(0.0f, -q8, kFingerZ));
       V3 g = mk(ref.cube0[0], ref.cube0[1], ref.cube0[2]);
       if (!second) g.z += c.pre_height_diff;
       else {
@@ -511,7 +572,7 @@ DEV float panda_cost(const PandaEnv& e, const PandaParams& P, const RolloutCfg& 
       }
       const V3 d = mk((lf.x + rf.x) / 2.0f - g.x, (lf.y + rf.y) / 2.0f - g.y, (lf.z + rf.z) / 2.0f - g.z);
       const float reach = sqrtf(dot(d, d));
-      const M33 C = ref_rotmat(e.cube[0].qx, e.cube[0].qy, e.cube[0].qz, e.cube[0].qw);
+      const M33 C = ref_rotmat(cubeA.qx, cubeA.qy, cubeA.qz, cubeA.qw);
       float cost_z;
       if (!second) cost_z = min_axis_cost(H.R.cz, C);
       else cost_z = fabsf(c.tilt_cos - dot(H.R.cz, col(C, ref.sel_axis)));
@@ -519,21 +580,26 @@ DEV float panda_cost(const PandaEnv& e, const PandaParams& P, const RolloutCfg& 
       return 10.0f * reach + 3.0f * tilt;
     }
     case M3P2I_TASK_PICK: {
-      const V3 d = mk(c.goal[0] - e.cube[0].p.x, c.goal[1] - e.cube[0].p.y, c.goal[2] - e.cube[0].p.z);
-      const M33 C = ref_rotmat(e.cube[0].qx, e.cube[0].qy, e.cube[0].qz, e.cube[0].qw);
+      const V3 d = mk(c.goal[0] - cubeA.p.x, c.goal[1] - cubeA.p.y, c.goal[2] - cubeA.p.z);
+      const M33 C = ref_rotmat(cubeA.qx, cubeA.qy, cubeA.qz, cubeA.qw);
       const M33 G = ref_rotmat(c.goal[3], c.goal[4], c.goal[5], c.goal[6]);
       const float ori = min_axis_cost(G.cx, C) + min_axis_cost(G.cy, C);
-      return 10.0f * sqrtf(dot(d, d)) + 15.0f * ori + panda_motion_cost(e);
+      return 10.0f * sqrtf(dot(d, d)) + 15.0f * ori + motion_cost;
     }
     case M3P2I_TASK_PLACE: {
-      Hand H;
-      panda_hand(P, e.q, e.qd, false, H);
-      const V3 lf = H.p + mul(H.R, mk(0.0f, e.q[7], kFingerZ)), rf = H.p + mul(H.R, mk(0.0f, -e.q[8], kFingerZ));
+      const V3 lf = H.p + mul(H.R, mk(0.0f, q7, kFingerZ)), rf = H.p + mul(H.R, mk(0.0f, -q8, kFingerZ));
       const V3 d = lf - rf;
       return 2.0f * (1.0f - sqrtf(dot(d, d)));
     }
     default: return 0.0f;
   }
+}
+
+DEV float panda_cost(const PandaEnv& e, const PandaParams& P, const RolloutCfg& c, int kg, const PandaRef& ref) {
+  Hand H;
+  H.p = mk(0, 0, 0); H.R.cx = mk(1, 0, 0); H.R.cy = mk(0, 1, 0); H.R.cz = mk(0, 0, 1); H.v = mk(0, 0, 0); H.w = mk(0, 0, 0);
+  if (c.task != M3P2I_TASK_PICK) panda_hand(P, e.q, e.qd, false, H);
+  return panda_cost_from_hand(H, e.q[7], e.q[8], e.cube[0], panda_motion_cost(e), c, kg, ref);
 }
 
 }  // namespace m3

@@ -1,16 +1,23 @@
-// panda_team.cuh — lane-cooperative Panda step: a TEAM of 16 lanes advances ONE sample.
+// panda_team.cuh — lane-cooperative Panda rollout: a TEAM of 16 lanes advances ONE sample.
 //
 // Why: at the sizes the planner runs at (K = 4096 samples) a thread-per-sample rollout is one warp per SM walking a
-// ~23 k-instruction serial chain per step, with 3/4 of the SM sub-partitions idle. The work inside a sample is mostly
+// ~20 k-instruction serial chain per step, with 3/4 of the SM sub-partitions idle. The work inside a sample is mostly
 // contact detection (independent per box corner) and Gauss-Seidel impulse solves (serial per body, but the two cubes
 // are independent of each other). A team splits it like this:
 //     lane bit 3  (g) : which cube the lane works for (0 = cubeA, 1 = cubeB); each 8-lane group keeps a replica of
 //                       "its" cube's state and applies that cube's impulses in lock-step
 //     lane bits 0-2 (c): which box corner the lane tests
-// Joint state, forward kinematics and the link boxes are replicated in all 16 lanes. Contact detection runs on all
-// corners at once; the solves are broadcast (warp shuffles) and applied in exactly the pair / corner order of the
-// thread-per-sample code (panda_env.cuh), so both produce the same trajectory up to fp32 summation order of the
-// reported contact forces. All branches that contain shuffles are warp-uniform (decided by __ballot_sync/__any_sync).
+// Joint state, forward kinematics and the link boxes are replicated in all 16 lanes (drives, sin/cos and the Philox
+// blocks are computed by one lane each and broadcast). Contact detection runs on all corners at once; the solves are
+// broadcast (warp shuffles) and applied in exactly the pair / corner order of the thread-per-sample code
+// (panda_env.cuh), so both produce the same trajectory up to fp32 rounding of reordered sums.
+// All branches that contain shuffles are warp-uniform (decided by __ballot_sync / __any_sync).
+//
+// Code size is a first-order concern here: with ~14 resident warps per SM at different program counters the kernel
+// is instruction-fetch bound as soon as its loop body outgrows the instruction cache (ncu: 75 % `no_inst` stalls with
+// the unrolled version in contact-rich states). Hence ONE copy of everything: one forward-kinematics site per
+// sub-step (the cost of step t is evaluated from the FK of the first sub-step of step t+1 — same joint positions),
+// link / cube pairs and the two detection directions as rolled loops, one inlined copy of each contact solve.
 #pragma once
 #include "panda_env.cuh"
 
@@ -22,6 +29,7 @@ constexpr unsigned kFull = 0xffffffffu;
 DEV V3 shfl3(V3 a, int src) {
   return mk(__shfl_sync(kFull, a.x, src), __shfl_sync(kFull, a.y, src), __shfl_sync(kFull, a.z, src));
 }
+DEV V3 sel3(bool c, V3 a, V3 b) { return mk(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
 
 struct TeamLane {
   int lane, g, c;     // lane in warp, cube group, corner
@@ -79,8 +87,7 @@ struct TeamEnv {
   DEV float4 state_row() const { return make_float4(q[0], qd[0], q[1], qd[1]); }
 };
 
-// The generic two-body solve is only reached when a cube touches the other cube or the gripper; keeping one
-// out-of-line copy keeps the hot loop small enough for the instruction cache.
+// The generic two-body solve is only reached when the two cubes touch each other; one out-of-line copy.
 __device__ __noinline__ V3 solve_contact3_call(Dyn3& A, Dyn3& B, V3 n, float depth, V3 c, float mu, float h,
                                                const PandaParams& P) {
   return solve_contact3(A, B, n, depth, c, mu, h, P);
@@ -93,13 +100,12 @@ DEV Dyn3 dyn_cube(V3 v, V3 w, V3 x, float im, float ii) {
 }
 
 // Serial application of the contacts found by the lanes [src0, src0+8): for corner j = 0..7 in order, the lane that
-// found a hit broadcasts (n, depth, p) and every lane for which `mine` holds applies solve(A, B, sign*n, ...).
-// Returns the sum of the impulses applied to A. The loop bounds and the shuffles are warp-uniform.
+// found a hit broadcasts (n, depth, p) and every lane for which `mine` holds applies solve(n, depth, p).
+// Returns the sum of the impulses the solves report. The loop bounds and the shuffles are warp-uniform.
 template <typename Solve>
-DEV V3 apply_hits(bool hit, V3 n, float depth, V3 p, int lane, int src0, bool mine, Solve&& solve) {
+DEV V3 apply_hits(bool hit, V3 n, float depth, V3 p, int src0, bool mine, Solve&& solve) {
   const unsigned hb = __ballot_sync(kFull, hit);
   V3 acc = mk(0, 0, 0);
-  if (!hb) return acc;
   // corners that hit in ANY 8-lane group of the warp, visited in ascending corner order
   unsigned todo = (hb | (hb >> 8) | (hb >> 16) | (hb >> 24)) & 0xffu;
   while (todo) {
@@ -114,28 +120,95 @@ DEV V3 apply_hits(bool hit, V3 n, float depth, V3 p, int lane, int src0, bool mi
   return acc;
 }
 
-DEV void team_panda_step(TeamEnv& e, const PandaParams& P, const float* u, float dt, int substeps, int passes,
-                         const TeamLane& t) {
-  const float h = dt / (float)substeps;
-  const float D = P.drive_damping;
+// hand pose + twist; sin/cos of joint j are computed by lane j of the team (one sincosf site) and broadcast
+DEV void team_fk(const PandaParams& P, const float* q, const float* qd, const TeamLane& t, Hand& H) {
+  const int j = min(t.lane & 15, 6);
+  float qj = q[0];
+#pragma unroll
+  for (int i = 1; i < 7; ++i) { if (j == i) qj = q[i]; }
+  float snj, csj;
+  sincosf(qj, &snj, &csj);
+  V3 p = mk(P.base[0], P.base[1], P.base[2]);
+  M33 R = {mk(1, 0, 0), mk(0, 1, 0), mk(0, 0, 1)};
+  V3 v = mk(0, 0, 0), w = mk(0, 0, 0);
+  constexpr float X[7] = {0.0f, 0.0f, 0.0f, 0.0825f, -0.0825f, 0.0f, 0.088f};
+  constexpr float Y[7] = {0.0f, 0.0f, -0.316f, 0.0f, 0.384f, 0.0f, 0.0f};
+  constexpr float Z[7] = {0.333f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  constexpr int ROLL[7] = {0, -1, 1, 1, -1, 1, 1};
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const float sn = __shfl_sync(kFull, snj, t.team_base + i), cs = __shfl_sync(kFull, csj, t.team_base + i);
+    const V3 d = mul(R, mk(X[i], Y[i], Z[i]));
+    v = v + cross(w, d);
+    p = p + d;
+    if (ROLL[i] == 1) { const V3 c1 = R.cy; R.cy = R.cz; R.cz = -c1; }
+    if (ROLL[i] == -1) { const V3 c1 = R.cy; R.cy = -R.cz; R.cz = c1; }
+    w = w + qd[i] * R.cz;
+    const V3 c0 = R.cx, c1 = R.cy;
+    R.cx = cs * c0 + sn * c1;
+    R.cy = cs * c1 - sn * c0;
+  }
+  const V3 d = kHandZ * R.cz;
+  v = v + cross(w, d);
+  p = p + d;
+  const V3 c0 = R.cx, c1 = R.cy;
+  R.cx = kHandYawC * c0 + kHandYawS * c1;
+  R.cy = kHandYawC * c1 - kHandYawS * c0;
+  H.p = p; H.R = R; H.v = v; H.w = w;
+}
+
+// The whole rollout of one sample by one team. `k` = row of the sample in this shard's buffers (or -1 for a producer
+// team replaying a row of another shard), `kg` its global id. Producer teams publish refs instead of costs.
+DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBufs& b, const TeamLane& t, int k, int kg,
+                      bool valid, bool producer, int which) {
+  constexpr int NU = 9;
+  const int K = c.K, T = c.T, ns = c.substeps;
+  const bool writer = valid && (t.lane & (kTeam - 1)) == 0;
+  const bool use_refs = b.refs != nullptr;
   const int g = t.g;
+  const float h = c.dt / (float)ns, D = P.drive_damping;
   const float im = 1.0f / P.cube_mass[g], ii = 1.0f / P.cube_inertia[g], mu_c = P.cube_mu[g];
   const float imo = 1.0f / P.cube_mass[g ^ 1], iio = 1.0f / P.cube_inertia[g ^ 1];
   const V3 half_own = mk(P.cube_half[g][0], P.cube_half[g][1], P.cube_half[g][2]);
   const V3 half_oth = mk(P.cube_half[g ^ 1][0], P.cube_half[g ^ 1][1], P.cube_half[g ^ 1][2]);
   const float rad_own = sqrtf(dot(half_own, half_own)), rad_oth = sqrtf(dot(half_oth, half_oth));
-  // group-partial impulse sums (identical in the 8 lanes of a group), lane-partial penalty sums
+
+  TeamEnv e;
+  if (c.env_live && k >= 0) e.load(b.env, K, k, g);
+  else e.load(b.base, 1, 0, g);
+  float run = 0.0f, J = 0.0f, gam = 1.0f;
+  float u[NU];
+#pragma unroll
+  for (int d = 0; d < NU; ++d) u[d] = 0.0f;
+  // group-partial impulse sums (identical in the 8 lanes of a group), lane-partial penalty sums, per step
   V3 imp_table = mk(0, 0, 0), imp_shelf = mk(0, 0, 0), imp_cubeb = mk(0, 0, 0), pen = mk(0, 0, 0);
-  for (int s = 0; s < substeps; ++s) {
-    // 1. joint drives: lane j of the team integrates joint j, the nine results are broadcast
-    {
+
+  const int n_iter = T * ns;
+#pragma unroll 1
+  for (int it = 0; it <= n_iter; ++it) {
+    const int step = it / ns, s = it - step * ns;
+    const bool last = it == n_iter;
+    if (s == 0 && !last) {
+      // ---- perturbed action of this step (mppi.py:392-416)
+      if (c.noise_mode == M3P2I_NOISE_PHILOX && !c.open_loop) {
+        // the three Philox blocks (dims 0-3, 4-7, 8) are drawn by lanes 0..2 of the team and broadcast
+        float z[4];
+        normal4(c.seed_lo, c.seed_hi, (uint32_t)kg, (uint32_t)step, (uint32_t)min(t.lane & 15, 2), z);
+        float zz[NU];
+#pragma unroll
+        for (int d = 0; d < NU; ++d) zz[d] = __shfl_sync(kFull, z[d & 3], t.team_base + (d >> 2));
+        perturb_action<NU>(c, b, kg, step, zz, u);
+      } else {
+        sample_action<NU>(c, b, kg, k, step, u);
+      }
+      imp_table = mk(0, 0, 0); imp_shelf = mk(0, 0, 0); imp_cubeb = mk(0, 0, 0); pen = mk(0, 0, 0);
+    }
+    if (!last) {
+      // ---- 1. joint drives: lane j of the team integrates joint j, the nine results are broadcast
       const int j = min(t.lane & 15, 8);
-      float qj = e.q[0], vj = e.qd[0];
+      float qj = e.q[0], vj = e.qd[0], uj = u[0];
 #pragma unroll
-      for (int i = 1; i < 9; ++i) { if (j == i) { qj = e.q[i]; vj = e.qd[i]; } }
-      float uj = u[0];
-#pragma unroll
-      for (int i = 1; i < 9; ++i) { if (j == i) uj = u[i]; }
+      for (int i = 1; i < 9; ++i) { if (j == i) { qj = e.q[i]; vj = e.qd[i]; uj = u[i]; } }
       const float m = j < 7 ? P.arm_inertia : P.finger_mass;
       float vs = (m * vj + h * D * uj) / (m + h * D);
       const float f = D * (uj - vs);
@@ -147,23 +220,50 @@ DEV void team_panda_step(TeamEnv& e, const PandaParams& P, const float* u, float
 #pragma unroll
       for (int i = 0; i < 9; ++i) e.qd[i] = __shfl_sync(kFull, vs, t.team_base + i);
     }
-    // 2. gravity on the group's cube
-    e.cu.v.z -= P.gravity * h;
-    // 3. geometry of this sub-step (positions are fixed until step 4)
+    // ---- forward kinematics at the current joint positions (the only FK site)
     Hand H;
-    panda_hand(P, e.q, e.qd, true, H);
-    OBox3 lbox[3];
+    team_fk(P, e.q, e.qd, t, H);
+
+    if (s == 0 && step > 0) {
+      // ---- cost of the step that just ended (same joint positions as this FK; the drives only changed velocities)
+      const int ps = step - 1;
+      if (producer) {
+        if ((t.lane & 15) == 0 && (which == 0 || c.multi_modal)) ref_publish(b, which, ps, c.epoch, e.cu, !c.multi_modal);
+      } else {
+        const int src = t.team_base;  // a lane of group 0 holds cubeA
+        Cube a;
+        a.p = shfl3(e.cu.p, src);
+        a.qx = __shfl_sync(kFull, e.cu.qx, src); a.qy = __shfl_sync(kFull, e.cu.qy, src);
+        a.qz = __shfl_sync(kFull, e.cu.qz, src); a.qw = __shfl_sync(kFull, e.cu.qw, src);
+        a.v = mk(0, 0, 0); a.w = mk(0, 0, 0);
+        PandaRef ref;
+        if (use_refs) ref = ref_wait(b, ps, c.epoch, c.multi_modal != 0);
+        else { ref.cube0[0] = a.p.x; ref.cube0[1] = a.p.y; ref.cube0[2] = a.p.z; ref.sel_axis = sel_axis_of(a); }
+        const float fx = e.f_table.x + 4.0f * e.f_shelf.x + e.f_cubeb.x, fy = e.f_table.y + 4.0f * e.f_shelf.y + e.f_cubeb.y;
+        const float motion = (fabsf(fx) + fabsf(fy)) > 0.1f ? 1000.0f : 0.0f;
+        const float cost = panda_cost_from_hand(H, e.q[7], e.q[8], a, motion, c, kg, ref);
+        run += cost;
+        J += gam * cost;
+        gam *= c.gamma;
+        if (writer) b.cost_h[(size_t)ps * K + k] = cost;
+      }
+    }
+    if (last) break;
+
+    // ---- 2. gravity on the group's cube
+    e.cu.v.z -= P.gravity * h;
+    // ---- 3. geometry of this sub-step (positions are fixed until step 4)
+    V3 lc[3];  // centres of the left-finger, right-finger and hand boxes
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
       const float* cen = f < 2 ? P.finger_center : P.hand_center;
-      const float* hf = f < 2 ? P.finger_half : P.hand_half;
       V3 l = mk(cen[0], cen[1], cen[2]);
       if (f == 0) { l.y += e.q[7]; l.z += kFingerZ; }
       if (f == 1) { l.y = -l.y - e.q[8]; l.z += kFingerZ; }
-      lbox[f].c = H.p + mul(H.R, l);
-      lbox[f].R = H.R;
-      lbox[f].half = mk(hf[0], hf[1], hf[2]);
+      lc[f] = H.p + mul(H.R, l);
     }
+    const V3 fhalf = mk(P.finger_half[0], P.finger_half[1], P.finger_half[2]);
+    const V3 hhalf = mk(P.hand_half[0], P.hand_half[1], P.hand_half[2]);
     float slide[2] = {e.qd[7], e.qd[8]};
     OBox3 cb;  // own cube
     cb.c = e.cu.p; cb.R = quat_to_R(e.cu.qx, e.cu.qy, e.cu.qz, e.cu.qw); cb.half = half_own;
@@ -179,42 +279,46 @@ DEV void team_panda_step(TeamEnv& e, const PandaParams& P, const float* u, float
       cc_near = dot(d, d) <= r * r;  // cheap symmetric pre-test; the exact test follows if it passes
     }
     OBox3 ob;
-    ob.c = xo; ob.half = half_oth;
-    ob.R = cb.R;
+    ob.c = xo; ob.half = half_oth; ob.R = cb.R;
     if (__any_sync(kFull, cc_near)) {
       ob.R.cx = shfl3(cb.R.cx, t.lane ^ 8); ob.R.cy = shfl3(cb.R.cy, t.lane ^ 8); ob.R.cz = shfl3(cb.R.cz, t.lane ^ 8);
       // exact test of the thread-per-sample code: sphere of cubeA against the box of cubeB
       cc_near = cc_near && (g == 0 ? boxes_near(cb, ob, P.contact_margin) : boxes_near(ob, cb, P.contact_margin));
     }
-    // link / cube proximity: pair (f, i) is handled by group i
-    bool lnear[3];
-#pragma unroll
-    for (int f = 0; f < 3; ++f) lnear[f] = boxes_near(lbox[f], cb, P.contact_margin);
-
-    // which fixed boxes are close to the own cube (bit k), decided once per sub-step
+    // which fixed boxes / link boxes are close to the own cube, decided once per sub-step
     unsigned near_mask = 0u;
-    for (int k = 0; k < P.n_static; ++k)
-      if (boxes_near(cb, obox_of(P.st[k]), P.contact_margin)) near_mask |= 1u << k;
+#pragma unroll 1
+    for (int ks = 0; ks < P.n_static; ++ks)
+      if (boxes_near(cb, obox_of(P.st[ks]), P.contact_margin)) near_mask |= 1u << ks;
     unsigned near_any = near_mask;
 #pragma unroll
     for (int o = 8; o < 32; o <<= 1) near_any |= __shfl_xor_sync(kFull, near_any, o);
+    unsigned lnear = 0u;
+#pragma unroll 1
+    for (int f = 0; f < 3; ++f) {
+      OBox3 lb;
+      lb.c = f == 0 ? lc[0] : (f == 1 ? lc[1] : lc[2]); lb.R = H.R; lb.half = f < 2 ? fhalf : hhalf;
+      if (boxes_near(lb, cb, P.contact_margin)) lnear |= 1u << f;
+    }
 
-    for (int p = 0; p < passes; ++p) {
+#pragma unroll 1
+    for (int p = 0; p < c.passes; ++p) {
       // (a) own cube against the fixed boxes
+#pragma unroll 1
       for (unsigned todo_k = near_any; todo_k; todo_k &= todo_k - 1) {
-        const int k = __ffs(todo_k) - 1;
-        const OBox3 sb = obox_of(P.st[k]);
-        const bool near = (near_mask >> k) & 1u;
+        const int ks = __ffs(todo_k) - 1;
+        const OBox3 sb = obox_of(P.st[ks]);
+        const bool near = (near_mask >> ks) & 1u;
         V3 n = mk(0, 0, 0);
         float depth = 0.0f;
         const bool hit = near && point_in_box(pc, sb, P.contact_margin, n, depth);
-        const float mu = 0.5f * (mu_c + P.st[k].mu);
-        const V3 got = apply_hits(hit, n, depth, pc, t.lane, t.group_base, true, [&](V3 nj, float dj, V3 pj) {
+        const float mu = 0.5f * (mu_c + P.st[ks].mu);
+        const V3 got = apply_hits(hit, n, depth, pc, t.group_base, true, [&](V3 nj, float dj, V3 pj) {
           return solve_cube_static(v, w, im, ii, x, nj, dj, pj, mu, h, P);
         });
         // impulses received by the fixed box = -(impulses on the cube)
-        if (k == P.idx_table) imp_table = imp_table - got;
-        if (k == P.idx_shelf) imp_shelf = imp_shelf - got;
+        if (ks == P.idx_table) imp_table = imp_table - got;
+        if (ks == P.idx_shelf) imp_shelf = imp_shelf - got;
         if (g == 1) imp_cubeb = imp_cubeb + got;
       }
       // (b) cubeA against cubeB, both ways; every lane of the team applies every impulse to replicas of both cubes
@@ -223,18 +327,19 @@ DEV void team_panda_step(TeamEnv& e, const PandaParams& P, const float* u, float
         Dyn3 A = g == 0 ? dyn_cube(v, w, x, im, ii) : dyn_cube(vo, wo, xo, imo, iio);   // cubeA
         Dyn3 B = g == 0 ? dyn_cube(vo, wo, xo, imo, iio) : dyn_cube(v, w, x, im, ii);   // cubeB
         const float mu = 0.5f * (P.cube_mu[0] + P.cube_mu[1]);
-        V3 n = mk(0, 0, 0);
-        float depth = 0.0f;
-        // corners of cubeA in cubeB (found by group 0), normal out of cubeB
-        bool hit = cc_near && g == 0 && point_in_box(pc, ob, P.contact_margin, n, depth);
-        V3 got = apply_hits(hit, n, depth, pc, t.lane, t.team_base, cc_near, [&](V3 nj, float dj, V3 pj) {
-          return solve_contact3_call(A, B, nj, dj, pj, mu, h, P);
-        });
-        // corners of cubeB in cubeA (found by group 1), normal out of cubeA -> solve with -n
-        hit = cc_near && g == 1 && point_in_box(pc, ob, P.contact_margin, n, depth);
-        got = got + apply_hits(hit, n, depth, pc, t.lane, t.team_base + 8, cc_near, [&](V3 nj, float dj, V3 pj) {
-          return solve_contact3_call(A, B, -nj, dj, pj, mu, h, P);
-        });
+        V3 got = mk(0, 0, 0);
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ++ph) {
+          // ph 0: corners of cubeA in cubeB (found by group 0), normal out of cubeB;
+          // ph 1: corners of cubeB in cubeA (found by group 1), normal out of cubeA -> solve with -n
+          V3 n = mk(0, 0, 0);
+          float depth = 0.0f;
+          const bool hit = cc_near && g == ph && point_in_box(pc, ob, P.contact_margin, n, depth);
+          const float sg = ph == 0 ? 1.0f : -1.0f;
+          got = got + apply_hits(hit, n, depth, pc, t.team_base + 8 * ph, cc_near, [&](V3 nj, float dj, V3 pj) {
+            return solve_contact3_call(A, B, sg * nj, dj, pj, mu, h, P);
+          });
+        }
         if (cc_near) {
           v = g == 0 ? A.v : B.v;
           w = g == 0 ? A.w : B.w;
@@ -242,41 +347,43 @@ DEV void team_panda_step(TeamEnv& e, const PandaParams& P, const float* u, float
         }
       }
       // (c) links against the cubes in the order (f, cubeA), (f, cubeB); pair (f, i) is worked by group i
-#pragma unroll
-      for (int f = 0; f < 3; ++f) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const bool mine = g == i && lnear[f];
+      if (__any_sync(kFull, lnear != 0u)) {
+#pragma unroll 1
+        for (int fi = 0; fi < 6; ++fi) {
+          const int f = fi >> 1, i = fi & 1;
+          const bool mine = g == i && ((lnear >> f) & 1u);
           if (!__any_sync(kFull, mine)) continue;
-          Dyn3 L;
-          L.v = H.v; L.w = H.w; L.x = H.p; L.im = 0.0f; L.ii = 0.0f;
-          if (f < 2) { L.axis = (f == 0 ? 1.0f : -1.0f) * H.R.cy; L.slide = slide[f]; L.ims = 1.0f / P.finger_mass; }
-          else { L.axis = mk(0, 0, 0); L.slide = 0.0f; L.ims = 0.0f; }
-          Dyn3 C = dyn_cube(v, w, x, im, ii);
+          OBox3 lb;
+          lb.c = f == 0 ? lc[0] : (f == 1 ? lc[1] : lc[2]); lb.R = H.R; lb.half = f < 2 ? fhalf : hhalf;
+          const V3 axis = f == 0 ? H.R.cy : (f == 1 ? -H.R.cy : mk(0, 0, 0));
+          const float ims = f < 2 ? 1.0f / P.finger_mass : 0.0f;
+          float sl_f = f == 0 ? slide[0] : (f == 1 ? slide[1] : 0.0f);
           const float mu = 0.5f * (P.robot_mu + mu_c);
-          V3 n = mk(0, 0, 0);
-          float depth = 0.0f;
-          // corners of the link box in the cube, normal out of the cube
-          const V3 lp = box_corner(lbox[f], t.c);
-          bool hit = mine && point_in_box(lp, cb, P.contact_margin, n, depth);
-          V3 got = apply_hits(hit, n, depth, lp, t.lane, t.team_base + 8 * i, mine, [&](V3 nj, float dj, V3 pj) {
-            return solve_contact3_call(L, C, nj, dj, pj, mu, h, P);
-          });
-          // corners of the cube in the link box, normal out of the link -> solve with -n
-          hit = mine && point_in_box(pc, lbox[f], P.contact_margin, n, depth);
-          got = got + apply_hits(hit, n, depth, pc, t.lane, t.team_base + 8 * i, mine, [&](V3 nj, float dj, V3 pj) {
-            return solve_contact3_call(L, C, -nj, dj, pj, mu, h, P);
-          });
-          if (mine) {
-            v = C.v; w = C.w;
-            if (i == 1) imp_cubeb = imp_cubeb - got;
+          const V3 lp = box_corner(lb, t.c);
+          V3 got = mk(0, 0, 0);
+#pragma unroll 1
+          for (int ph = 0; ph < 2; ++ph) {
+            // ph 0: corners of the link box in the cube, normal out of the cube;
+            // ph 1: corners of the cube in the link box, normal out of the link -> solve with -n
+            const V3 pt = ph == 0 ? lp : pc;
+            OBox3 bx;
+            bx.c = sel3(ph == 0, cb.c, lb.c); bx.half = sel3(ph == 0, cb.half, lb.half);
+            bx.R.cx = sel3(ph == 0, cb.R.cx, lb.R.cx); bx.R.cy = sel3(ph == 0, cb.R.cy, lb.R.cy);
+            bx.R.cz = sel3(ph == 0, cb.R.cz, lb.R.cz);
+            V3 n = mk(0, 0, 0);
+            float depth = 0.0f;
+            const bool hit = mine && point_in_box(pt, bx, P.contact_margin, n, depth);
+            const float sg = ph == 0 ? 1.0f : -1.0f;
+            got = got + apply_hits(hit, n, depth, pt, t.team_base + 8 * i, mine, [&](V3 nj, float dj, V3 pj) {
+              return solve_link_cube(H.v, H.w, H.p, axis, sl_f, ims, v, w, im, ii, x, sg * nj, dj, pj, mu, h, P);
+            });
           }
-          if (f < 2) {
-            // the finger's sliding speed is shared by both groups: take it from the group that worked the pair
-            const float sl = __shfl_sync(kFull, L.slide, t.team_base + 8 * i);
-            const bool worked = __shfl_sync(kFull, (int)mine, t.team_base + 8 * i) != 0;
-            if (worked) slide[f] = sl;
-          }
+          if (mine && i == 1) imp_cubeb = imp_cubeb - got;
+          // the finger's sliding speed is shared by both groups: take it from the group that worked the pair
+          const float sl = __shfl_sync(kFull, sl_f, t.team_base + 8 * i);
+          const bool worked = __shfl_sync(kFull, (int)mine, t.team_base + 8 * i) != 0;
+          if (worked && f == 0) slide[0] = sl;
+          if (worked && f == 1) slide[1] = sl;
         }
       }
     }
@@ -292,15 +399,18 @@ DEV void team_panda_step(TeamEnv& e, const PandaParams& P, const float* u, float
       if (ks >= 0) {
         const OBox3 sb = obox_of(P.st[ks]);
         const float mu = 0.5f * (P.robot_mu + P.st[ks].mu);
-#pragma unroll
+#pragma unroll 1
         for (int f = 0; f < 3; ++f) {
-          if (!boxes_near(lbox[f], sb, 0.0f)) continue;
-          const V3 lp = box_corner(lbox[f], t.c);
+          OBox3 lb;
+          lb.c = f == 0 ? lc[0] : (f == 1 ? lc[1] : lc[2]); lb.R = H.R; lb.half = f < 2 ? fhalf : hhalf;
+          if (!boxes_near(lb, sb, 0.0f)) continue;
+          const V3 lp = box_corner(lb, t.c);
           V3 n; float depth;
           if (!point_in_box(lp, sb, 0.0f, n, depth)) continue;
           const float fn = P.penalty_stiffness * depth;
           V3 vel = H.v + cross(H.w, lp - H.p);
-          if (f < 2) vel = vel + slide[f] * ((f == 0 ? 1.0f : -1.0f) * H.R.cy);
+          if (f == 0) vel = vel + slide[0] * H.R.cy;
+          if (f == 1) vel = vel - slide[1] * H.R.cy;
           const float vn = dot(vel, n);
           const V3 tv = vel - vn * n;
           const float vt = sqrtf(dot(tv, tv));
@@ -310,7 +420,7 @@ DEV void team_panda_step(TeamEnv& e, const PandaParams& P, const float* u, float
         }
       }
     }
-    // 4. positions
+    // ---- 4. positions
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
       float qn = e.q[j] + h * e.qd[j];
@@ -319,50 +429,47 @@ DEV void team_panda_step(TeamEnv& e, const PandaParams& P, const float* u, float
       e.q[j] = qn;
     }
     {
-      Cube& c = e.cu;
-      c.p = c.p + h * c.v;
-      const float qx = c.qx, qy = c.qy, qz = c.qz, qw = c.qw, hh = 0.5f * h;
-      const float nx = qx + hh * (c.w.x * qw + c.w.y * qz - c.w.z * qy);
-      const float ny = qy + hh * (c.w.y * qw + c.w.z * qx - c.w.x * qz);
-      const float nz = qz + hh * (c.w.z * qw + c.w.x * qy - c.w.y * qx);
-      const float nw = qw - hh * (c.w.x * qx + c.w.y * qy + c.w.z * qz);
+      Cube& cu = e.cu;
+      cu.p = cu.p + h * cu.v;
+      const float qx = cu.qx, qy = cu.qy, qz = cu.qz, qw = cu.qw, hh = 0.5f * h;
+      const float nx = qx + hh * (cu.w.x * qw + cu.w.y * qz - cu.w.z * qy);
+      const float ny = qy + hh * (cu.w.y * qw + cu.w.z * qx - cu.w.x * qz);
+      const float nz = qz + hh * (cu.w.z * qw + cu.w.x * qy - cu.w.y * qx);
+      const float nw = qw - hh * (cu.w.x * qx + cu.w.y * qy + cu.w.z * qz);
       const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
-      c.qx = nx * inv; c.qy = ny * inv; c.qz = nz * inv; c.qw = nw * inv;
+      cu.qx = nx * inv; cu.qy = ny * inv; cu.qz = nz * inv; cu.qw = nw * inv;
+    }
+    if (s == ns - 1) {
+      // ---- end of the step: reported contact forces, per-step stores
+      V3 pr = pen;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) pr = pr + shfl3(pr, t.lane ^ o);
+      const V3 pen_o = shfl3(pr, t.lane ^ 8);
+      const V3 pen_table = g == 0 ? pr : pen_o, pen_shelf = g == 0 ? pen_o : pr;
+      const V3 it_o = shfl3(imp_table, t.lane ^ 8), is_o = shfl3(imp_shelf, t.lane ^ 8), ib_o = shfl3(imp_cubeb, t.lane ^ 8);
+      const V3 itab = g == 0 ? imp_table + it_o : it_o + imp_table;   // cubeA's share first, as in the serial order
+      const V3 ishf = g == 0 ? imp_shelf + is_o : is_o + imp_shelf;
+      const V3 icb = g == 1 ? imp_cubeb : ib_o;
+      const float inv_dt = 1.0f / c.dt, inv_ns = 1.0f / (float)ns;
+      e.f_table = inv_dt * itab + inv_ns * pen_table;
+      e.f_shelf = inv_dt * ishf + inv_ns * pen_shelf;
+      e.f_cubeb = inv_dt * icb;
+      if (writer) {
+#pragma unroll
+        for (int d = 0; d < NU; ++d) b.actions[(size_t)(step * NU + d) * K + k] = u[d];
+        b.states[(size_t)step * K + k] = e.state_row();
+      }
     }
   }
-  // reduce the lane-partial penalties over the 8 lanes of each group, then combine the two groups
+  if (producer) return;
+  if (writer) { b.J[k] = J; b.cost_sum[k] = run; }
+  if (c.store_env && valid) {
+    e.store(b.env, K, k, t);
+    if (writer) {
 #pragma unroll
-  for (int o = 1; o < 8; o <<= 1) pen = pen + shfl3(pen, t.lane ^ o);
-  const V3 pen_o = shfl3(pen, t.lane ^ 8);
-  const V3 pen_table = g == 0 ? pen : pen_o, pen_shelf = g == 0 ? pen_o : pen;
-  const V3 it_o = shfl3(imp_table, t.lane ^ 8), is_o = shfl3(imp_shelf, t.lane ^ 8), ib_o = shfl3(imp_cubeb, t.lane ^ 8);
-  const V3 it = g == 0 ? imp_table + it_o : it_o + imp_table;   // cubeA's share first, as in the serial order
-  const V3 is = g == 0 ? imp_shelf + is_o : is_o + imp_shelf;
-  const V3 ib = g == 1 ? imp_cubeb : ib_o;
-  const float inv_dt = 1.0f / dt, inv_ns = 1.0f / (float)substeps;
-  e.f_table = inv_dt * it + inv_ns * pen_table;
-  e.f_shelf = inv_dt * is + inv_ns * pen_shelf;
-  e.f_cubeb = inv_dt * ib;
-}
-
-// task cost of the sample, identical in all lanes of the team (cubeA's pose is fetched from group 0)
-DEV float team_panda_cost(const TeamEnv& e, const PandaParams& P, const RolloutCfg& c, int kg, const PandaRef* ref,
-                          const TeamLane& t) {
-  PandaEnv full;
-#pragma unroll
-  for (int j = 0; j < 9; ++j) { full.q[j] = e.q[j]; full.qd[j] = e.qd[j]; }
-  const int src = t.team_base;  // a lane of group 0 holds cubeA
-  Cube a;
-  a.p = shfl3(e.cu.p, src);
-  a.qx = __shfl_sync(kFull, e.cu.qx, src); a.qy = __shfl_sync(kFull, e.cu.qy, src);
-  a.qz = __shfl_sync(kFull, e.cu.qz, src); a.qw = __shfl_sync(kFull, e.cu.qw, src);
-  a.v = mk(0, 0, 0); a.w = mk(0, 0, 0);
-  full.cube[0] = a; full.cube[1] = a;
-  full.f_table = e.f_table; full.f_shelf = e.f_shelf; full.f_cubeb = e.f_cubeb;
-  PandaRef r;
-  if (ref) r = *ref;
-  else { r.cube0[0] = a.p.x; r.cube0[1] = a.p.y; r.cube0[2] = a.p.z; r.sel_axis = sel_axis_of(a); }
-  return panda_cost(full, P, c, kg, r);
+      for (int d = 0; d < NU; ++d) b.vel_target[(size_t)d * K + k] = u[d];
+    }
+  }
 }
 
 }  // namespace m3

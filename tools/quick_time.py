@@ -6,11 +6,12 @@ sys.path.insert(0, os.path.join(ROOT, "m3p2i-aip_b200")); sys.path.insert(0, ROO
 from m3p2i_b200 import _abi as A, native, scene as S
 import bench
 
-def run(env, task, K, T, mm=False, goal=None, robot=None, grip=None):
+def run(env, task, K, T, mm=False, goal=None, robot=None, grip=None, q=None):
     cfg = S.make_cfg(env, task, goal, K, T, multi_modal=mm)
     if env == "panda_env":
         dof, root, g = bench.scene_inputs(); sc = S.build_panda_scene()
         if task != "pick": g = np.zeros(7, np.float32)
+        if q is not None: dof = dof.copy(); dof[0::2] = q
     else:
         actors = S.default_actors(env); dof, root = S.initial_dof_state(actors).copy(), S.initial_root_state(actors)
         if robot: dof[0], dof[2] = robot
@@ -28,6 +29,7 @@ def run(env, task, K, T, mm=False, goal=None, robot=None, grip=None):
 if __name__ == "__main__":
     print("M3P2I_ROLLOUT_BLOCK =", os.environ.get("M3P2I_ROLLOUT_BLOCK"))
     run("panda_env", "pick", 4096, 32, grip="close")
+    run("panda_env", "pick", 4096, 32, grip="close", q=[-0.21448, 1.040633, -0.091726, -1.527796, 0.144743, 2.56178, 0.807333, 0.027, 0.027])  # gripper closed around cubeA
     run("panda_env", "reach", 4096, 32, mm=True, grip="open")
     run("point_env", "navigation", 200, 12, goal=[-3.0, 3.0])
     run("point_env", "push", 1024, 20, goal=[-1.0, -1.0], robot=[0.2, 2.45])
