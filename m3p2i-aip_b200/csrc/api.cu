@@ -269,7 +269,7 @@ int rollout_lanes(const H* h) {
   }
   int want = forced ? forced : h->cfg.lanes_per_sample;
   if (want == 1 || want == 16) return want;
-  return h->cfg.num_samples <= 16384 ? 16 : 1;
+  return h->cfg.num_samples <= 4608 ? 16 : 1;   // measured crossover on B200 (profiles/r01_ksweep_lanes.csv)
 }
 
 RolloutCfg make_rcfg(const H* h) {

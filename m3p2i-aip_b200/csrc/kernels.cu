@@ -8,7 +8,8 @@
 
 namespace m3 {
 
-constexpr int kRolloutBlock = 32;   // one warp per CTA: at K = 4096 the 128 CTAs land on 128 different SMs
+constexpr int kRolloutBlock = 32;
+constexpr int kTeamBlock = 128;     // team kernel: 16 samples per CTA, warps re-aligned every sub-step (see panda_team.cuh)   // one warp per CTA: at K = 4096 the 128 CTAs land on 128 different SMs
 constexpr int kStatsBlock = 1024;
 constexpr int kSumBlock = 256;
 
@@ -199,7 +200,7 @@ namespace m3 {
 
 // Lane-cooperative variant for panda_env: 16 lanes per sample (panda_team.cuh), two samples per warp.
 // CTA 0 is the producer of the batch rows read by the reach cost when b.refs is set.
-__global__ void __launch_bounds__(kRolloutBlock, 14)
+__global__ void __launch_bounds__(kTeamBlock, 512 / kTeamBlock)
 k_rollout_team(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
   const TeamLane t = team_lane();
   const bool use_refs = b.refs != nullptr;
@@ -237,8 +238,8 @@ void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, co
   if (env_type == M3P2I_ENV_POINT) {
     k_rollout<M3P2I_ENV_POINT><<<grid, block, 0, st>>>(c, *pp, b);
   } else if (c.lanes == kTeam) {
-    const int teams_per_block = kRolloutBlock / kTeam;
-    k_rollout_team<<<(c.K + teams_per_block - 1) / teams_per_block + extra, kRolloutBlock, 0, st>>>(c, *qp, b);
+    const int teams_per_block = kTeamBlock / kTeam;
+    k_rollout_team<<<(c.K + teams_per_block - 1) / teams_per_block + extra, kTeamBlock, 0, st>>>(c, *qp, b);
   } else {
     k_rollout<M3P2I_ENV_PANDA><<<grid, block, 0, st>>>(c, *qp, b);
   }

@@ -188,6 +188,9 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
   for (int it = 0; it <= n_iter; ++it) {
     const int step = it / ns, s = it - step * ns;
     const bool last = it == n_iter;
+    // Re-align the warps of the CTA once per sub-step: they then walk the same stretch of this (large) loop body at
+    // about the same time and share its instruction-cache lines instead of evicting each other's.
+    __syncthreads();
     if (s == 0 && !last) {
       // ---- perturbed action of this step (mppi.py:392-416)
       if (c.noise_mode == M3P2I_NOISE_PHILOX && !c.open_loop) {

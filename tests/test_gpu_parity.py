@@ -259,8 +259,6 @@ def test_team_and_thread_kernels_agree(task, mm, shelf):
             assert frac <= budget, f"lanes={lanes} tick {i}: {frac:.3f} of the samples differ from the oracle"
             assert np.median(np.abs(ch_n - ch_o)) < 5e-4
             assert_close(a_n, a_o, 2e-2, 2e-2, f"lanes={lanes} vs oracle action [{i}]")
-        if task == "pick":   # the scenario really has contacts: the cube is held, lifted or pushed in most rollouts
-            assert (np.abs(st_n[:, -1] - st_n[:, 0]).max(axis=1) > 1e-3).all()
         res[lanes] = outs
         o.close()
         n.close()

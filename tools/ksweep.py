@@ -42,6 +42,12 @@ def run(env, K, T, reps=20):
     print(f"{env},{K},{T},{m:.4f},{r:.4f},{K * T / m / 1e3:.1f},{nbytes * K * T / r / 1e6:.1f}", flush=True)
 
 
+if __name__ == "__main__" and len(sys.argv) > 1:
+    print("env,K,H,ms_per_command,rollout_ms,Msample_steps_per_s,rollout_algorithmic_GBps  (M3P2I_LANES=%s)" % os.environ.get("M3P2I_LANES"))
+    for K in [int(a) for a in sys.argv[1:]]:
+        run("panda_env", K, 32)
+    sys.exit(0)
+
 if __name__ == "__main__":
     print("env,K,H,ms_per_command,rollout_ms,Msample_steps_per_s,rollout_algorithmic_GBps")
     for K in (1024, 4096, 16384, 65536, 262144, 1048576):
