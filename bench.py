@@ -293,7 +293,7 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_rollout<panda>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_rollout_team (panda_env, 16 lanes per sample)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(), "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_ncu_rollout_team_summary.csv)",
                          "algorithmic_bytes_per_launch": B_ROLLOUT * K_PER_GPU * HORIZON, "peak_source": peak_src,
                          "bytes_per_sample_step": B_ROLLOUT, "kernel_ms": r_ms,
