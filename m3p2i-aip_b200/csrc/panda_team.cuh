@@ -267,6 +267,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     }
     const V3 fhalf = mk(P.finger_half[0], P.finger_half[1], P.finger_half[2]);
     const V3 hhalf = mk(P.hand_half[0], P.hand_half[1], P.hand_half[2]);
+    const float frad = sqrtf(dot(fhalf, fhalf)), hrad = sqrtf(dot(hhalf, hhalf));
     float slide[2] = {e.qd[7], e.qd[8]};
     OBox3 cb;  // own cube
     cb.c = e.cu.p; cb.R = quat_to_R(e.cu.qx, e.cu.qy, e.cu.qz, e.cu.qw); cb.half = half_own;
@@ -289,18 +290,20 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       cc_near = cc_near && (g == 0 ? boxes_near(cb, ob, P.contact_margin) : boxes_near(ob, cb, P.contact_margin));
     }
     // which fixed boxes / link boxes are close to the own cube, decided once per sub-step
-    unsigned near_mask = 0u;
-#pragma unroll 1
-    for (int ks = 0; ks < P.n_static; ++ks)
-      if (boxes_near(cb, obox_of(P.st[ks]), P.contact_margin)) near_mask |= 1u << ks;
-    unsigned near_any = near_mask;
-#pragma unroll
-    for (int o = 8; o < 32; o <<= 1) near_any |= __shfl_xor_sync(kFull, near_any, o);
+    // lane c of a group tests fixed box c (n_static <= 8); the group's verdicts are collected with one ballot
+    const bool near_c = t.c < P.n_static && boxes_near(cb, obox_of(P.st[min(t.c, P.n_static - 1)]), P.contact_margin);
+    const unsigned near_bal = __ballot_sync(kFull, near_c);
+    const unsigned near_mask = (near_bal >> t.group_base) & 0xffu;
+    const unsigned near_any = (near_bal | (near_bal >> 8) | (near_bal >> 16) | (near_bal >> 24)) & 0xffu;
     unsigned lnear = 0u;
 #pragma unroll 1
     for (int f = 0; f < 3; ++f) {
       OBox3 lb;
       lb.c = f == 0 ? lc[0] : (f == 1 ? lc[1] : lc[2]); lb.R = H.R; lb.half = f < 2 ? fhalf : hhalf;
+      // centre-distance pre-test (a superset of the exact sphere-vs-box test below)
+      const V3 dl = lb.c - cb.c;
+      const float rr = (f < 2 ? frad : hrad) + rad_own + P.contact_margin;
+      if (dot(dl, dl) > rr * rr) continue;
       if (boxes_near(lb, cb, P.contact_margin)) lnear |= 1u << f;
     }
 
@@ -402,8 +405,12 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       if (ks >= 0) {
         const OBox3 sb = obox_of(P.st[ks]);
         const float mu = 0.5f * (P.robot_mu + P.st[ks].mu);
+        // one bounding sphere for hand + fingers first (centre = hand box centre, radius covers the three boxes)
+        OBox3 gb;
+        gb.c = lc[2]; gb.R = H.R; gb.half = mk(hrad + 0.12f, 0.0f, 0.0f);
+        const bool grip_near = boxes_near(gb, sb, 0.0f);
 #pragma unroll 1
-        for (int f = 0; f < 3; ++f) {
+        for (int f = 0; f < 3 && grip_near; ++f) {
           OBox3 lb;
           lb.c = f == 0 ? lc[0] : (f == 1 ? lc[1] : lc[2]); lb.R = H.R; lb.half = f < 2 ? fhalf : hhalf;
           if (!boxes_near(lb, sb, 0.0f)) continue;
