@@ -47,6 +47,21 @@ def scene_inputs():
     return dof, root, goal
 
 
+class stdout_to_stderr:
+    """NCCL prints its version banner on fd 1 during communicator creation; the driver wants exactly one JSON line
+    on stdout, so fd 1 is pointed at stderr while communicators are being built."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -200,7 +215,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
 
     Kg = K_PER_GPU * world
     cfg = S.make_cfg("panda_env", "pick", None, Kg, HORIZON)
@@ -209,9 +226,10 @@ def main():
     planner = native.NativePlanner(c, S.build_panda_scene(), device=local_rank)
     planner.set_filter_matrix(S.savgol_matrix(HORIZON))
     if world > 1:
-        uid = [native.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        planner.comm_init(rank, world, uid[0])
+        with stdout_to_stderr():
+            uid = [native.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            planner.comm_init(rank, world, uid[0])
     dof, root, goal = scene_inputs()
     planner.set_objective("pick", goal, "close")
     planner.set_state(dof, root)

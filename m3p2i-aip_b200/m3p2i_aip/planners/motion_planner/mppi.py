@@ -65,8 +65,8 @@ class MPPI():
         self._full_cfg = cfg
         m = cfg.mppi
         self.mppi_mode = getattr(m, "mppi_mode", "halton-spline")
-        if self.mppi_mode != "halton-spline":
-            raise NotImplementedError("mppi_mode='simple' is not used by any shipped configuration (mppi/*.yaml:4)")
+        if self.mppi_mode not in ("halton-spline", "simple"):
+            raise ValueError(f"unknown mppi_mode {self.mppi_mode!r}")
         self.sampling_method = getattr(m, "sampling_method", "halton")
         self.K = int(m.num_samples)
         self.half_K = int(self.K / 2)
@@ -103,6 +103,12 @@ class MPPI():
         obj = getattr(owner, "objective", None)
         from m3p2i_aip.planners.motion_planner.cost_functions import Objective
         from m3p2i_aip.utils.isaacgym_utils.isaacgym_wrapper import IsaacGymWrapper
+        self.noise_abs_cost = bool(getattr(m, "noise_abs_cost", False))
+        self.noise_sigma_inv = torch.inverse(self.noise_sigma)
+        self._rng = torch.Generator().manual_seed(self.seed_val)
+        self.U = None
+        if self.mppi_mode == "simple":
+            m.fused = False   # classic MPPI resamples its noise every call and runs through the callbacks
         self.fused = (isinstance(sim, IsaacGymWrapper) and isinstance(obj, Objective)
                       and getattr(running_cost, "__self__", None) is owner and getattr(m, "fused", True)
                       and sim.num_envs == self.K)
@@ -120,6 +126,15 @@ class MPPI():
             # the softmin/update kernels need no scene state, but the handle wants one
             actors = S.default_actors(self.env_type)
             self.backend.set_state(S.initial_dof_state(actors), S.initial_root_state(actors))
+            if self.mppi_mode == "simple":
+                # classic MPPI update = softmin of the TOTAL cost at temperature lambda and U <- sum_k w_k a_k
+                # (U + sum w (a - U) with sum w = 1): the same kernels with gamma = 1, step size 1, beta = lambda
+                c = S.build_config(cfg, noise_mode=A.NOISE_TABLE, seed=self.seed_val)
+                c.gamma, c.step_size_mean, c.multi_modal, c.filter_u = 1.0, 1.0, 0, 0
+                self.backend.close()
+                self.backend = native.NativePlanner(c, scene)
+                self.backend.set_state(S.initial_dof_state(actors), S.initial_root_state(actors))
+                self.U = self._sample_noise(self.T)
 
     # ------------------------------------------------------------------ noise table (mppi.py:386-392,458-483)
     @property
@@ -139,6 +154,11 @@ class MPPI():
             return torch.randn(sample_shape, self.T, self.nu, generator=g) * torch.sqrt(torch.diagonal(self.noise_sigma))
         raise ValueError(f"unknown sampling_method {self.sampling_method!r}")
 
+    def _sample_noise(self, *shape):
+        """N(0, noise_sigma) draws [*shape, nu] (MultivariateNormal of mppi.py:129-131, own generator)."""
+        L = torch.linalg.cholesky(self.noise_sigma)
+        return torch.randn(*shape, self.nu, generator=self._rng) @ L.T
+
     def _ensure_noise(self):
         if self.sampling_method == "philox" and self._delta is None:
             return
@@ -156,8 +176,12 @@ class MPPI():
         if not torch.is_tensor(state):
             state = torch.tensor(state)
         self.state = state.to(torch.float32)
-        self._ensure_noise()
         self._lazy = {}
+        if self.mppi_mode == "simple":
+            action, info = self._command_simple()
+            self._info = info
+            return action
+        self._ensure_noise()
         if self.fused:
             obj = self._objective
             if obj.task is None:
@@ -182,6 +206,56 @@ class MPPI():
         out = torch.roll(seq, -1, dims=0)
         out[-1] = seq[-1]
         return out
+
+    def _rollout_callbacks(self, act):
+        """The reference's T-step loop over the user's callbacks (mppi.py:296-315): -> cost_horizon, states, actions"""
+        K, T = self.K, self.T
+        state = self.state.view(1, -1).repeat(K, 1) if self.state.shape != (K, self.nx) else self.state
+        cost_horizon = torch.zeros(K, T)
+        states, actions = [], []
+        for t in range(T):
+            u = self.u_scale * act[:, t]
+            if self.sample_null_action:
+                u[K - 1] = 0.0
+            state, u = self._dynamics(state, u, t)
+            c = self._running_cost(state)
+            cost_horizon[:, t] = torch.as_tensor(c, dtype=torch.float32)
+            states.append(torch.as_tensor(state, dtype=torch.float32))
+            actions.append(torch.as_tensor(u, dtype=torch.float32))
+        return cost_horizon, torch.stack(states, dim=-2), torch.stack(actions, dim=-2)
+
+    def _command_simple(self):
+        """mppi_mode='simple' (mppi.py:220-233,335-363): fresh Gaussian noise, lambda * U Sigma^-1 eps control cost,
+        softmin of the total cost at temperature lambda. Rollouts run through the callbacks, the softmin and the
+        weighted sum through m3p2i_update_only."""
+        K, T, nu = self.K, self.T, self.nu
+        self.U = torch.roll(self.U, -1, dims=0)
+        noise = self._sample_noise(K, T)
+        u_min = torch.tensor(list(self.backend.cfg.u_min)[:nu])
+        u_max = torch.tensor(list(self.backend.cfg.u_max)[:nu])
+        act = torch.max(torch.min(self.U + noise, u_max), u_min)
+        if self.env_type == "panda_env" and self.gripper_command in ("open", "close"):
+            act[:, :, 7:9] = 1.5 if self.gripper_command == "open" else -1.5
+        cost_horizon, states, actions = self._rollout_callbacks(act)
+        if self.sample_null_action:
+            act[K - 1] = 0.0                              # perturbed_action[K-1] is overwritten by the null action (mppi.py:302)
+        cs = cost_horizon.sum(1)
+        cost_total = cs + cs.mean()                      # aliasing quirk, mppi.py:282-284,325
+        noise = act - self.U                              # bounded noise, mppi.py:356
+        ac = self.lambda_ * (noise.abs() if self.noise_abs_cost else noise) @ self.noise_sigma_inv
+        cost_total = cost_total + torch.sum(self.U * ac, dim=(1, 2))
+        st = self.backend.get_planner_state()
+        st.beta = float(self.lambda_)
+        self.backend.set_planner_state(st)
+        packed = torch.zeros(K, T)
+        packed[:, 0] = cost_total
+        new_U, info = self.backend.update_only(packed.numpy(), act.numpy())
+        self.U = torch.from_numpy(np.array(new_U, copy=True))
+        self._lazy.update(states=states, actions=actions / self.u_scale, cost_total=cost_total)
+        action = self.U[: self.u_per_command].clone()
+        if self.filter_u and action.shape[0] >= 9:
+            action = torch.from_numpy(S.savgol_matrix(action.shape[0]) @ action.numpy())
+        return action, info
 
     def _command_generic(self):
         """mppi.py:237-245,381-416,275-332 with the user's callbacks; update through the native library."""
@@ -208,20 +282,8 @@ class MPPI():
             act[self.half_K] = seqs["best_traj_2"]
         if self.env_type == "panda_env" and self.gripper_command in ("open", "close"):
             act[:, :, 7:9] = 1.5 if self.gripper_command == "open" else -1.5
-        state = self.state.view(1, -1).repeat(K, 1) if self.state.shape != (K, self.nx) else self.state
-        cost_horizon = torch.zeros(K, T)
-        states, actions = [], []
-        for t in range(T):
-            u = self.u_scale * act[:, t]
-            if self.sample_null_action:
-                u[K - 1] = 0.0
-            state, u = self._dynamics(state, u, t)
-            c = self._running_cost(state)
-            cost_horizon[:, t] = torch.as_tensor(c, dtype=torch.float32)
-            states.append(torch.as_tensor(state, dtype=torch.float32))
-            actions.append(torch.as_tensor(u, dtype=torch.float32))
-        actions = torch.stack(actions, dim=-2)
-        self._lazy["states"] = torch.stack(states, dim=-2)
+        cost_horizon, states, actions = self._rollout_callbacks(act)
+        self._lazy["states"] = states
         for k in _SEQ_KEYS:
             getattr(st, k)[: T * nu] = seqs[k].reshape(-1).tolist()
         self.backend.set_planner_state(st)
