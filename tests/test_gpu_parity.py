@@ -268,3 +268,21 @@ def test_team_and_thread_kernels_agree(task, mm, shelf):
             frac = _sample_mismatch(res[16][i][j], res[1][i][j], RTOL, ATOL)
             assert frac <= budget, f"team vs thread {what} [{i}]: {frac:.3f} of the samples differ"
             assert np.median(np.abs(res[16][i][j] - res[1][i][j])) < 5e-4
+
+
+@pytest.mark.parametrize("env,task,K,T", [("panda_env", "pick", 21, 9), ("panda_env", "reach", 20, 64), ("point_env", "push", 33, 64),
+                                          ("point_env", "navigation", 20, 9), ("panda_env", "place", 4609, 12)])
+def test_edge_sizes(env, task, K, T):
+    """Ragged sizes: K below one warp / not a multiple of a team pair or CTA, the minimum K (20, top-k) and T (9,
+    Savitzky-Golay window), the maximum horizon (64), and the first K handled by the thread-per-sample kernel."""
+    O.set_threads(8)
+    case = ("edge", env, task, [-1.0, -1.0] if env == "point_env" else None, K, T, False, False, [0.2, 2.45] if task == "push" else None)
+    cfg, o, n = _setup(case, A.NOISE_PHILOX)
+    for i in range(2):
+        a_o, c_o, _ = o.command()
+        a_n, c_n, _ = n.command()
+        assert_close(n.read_buffer(A.BUF_COST_HORIZON), o.read_buffer(A.BUF_COST_HORIZON), RTOL, ATOL, f"cost_horizon [{i}]", 0.01)
+        assert_close(a_n, a_o, 1e-2, 1e-2, f"action [{i}]")
+        assert np.isfinite(c_n).all()
+    o.close()
+    n.close()
