@@ -9,7 +9,7 @@
 namespace m3 {
 
 constexpr int kRolloutBlock = 32;
-constexpr int kTeamBlock = 128;     // team kernel: 16 samples per CTA, warps re-aligned every sub-step (see panda_team.cuh)   // one warp per CTA: at K = 4096 the 128 CTAs land on 128 different SMs
+constexpr int kTeamBlockMax = 256;  // team kernel: up to 8 warps (16 samples) per CTA, size chosen per launch (team_block)
 constexpr int kStatsBlock = 1024;
 constexpr int kSumBlock = 256;
 
@@ -200,7 +200,7 @@ namespace m3 {
 
 // Lane-cooperative variant for panda_env: 16 lanes per sample (panda_team.cuh), two samples per warp.
 // CTA 0 is the producer of the batch rows read by the reach cost when b.refs is set.
-__global__ void __launch_bounds__(kTeamBlock, 512 / kTeamBlock)
+__global__ void __launch_bounds__(kTeamBlockMax, 2)
 k_rollout_team(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
   const TeamLane t = team_lane();
   const bool use_refs = b.refs != nullptr;
@@ -230,6 +230,34 @@ static int rollout_block(int K) {
   return K <= 148 * 16 * 4 ? 16 : kRolloutBlock;
 }
 
+// CTA size of the team kernel. Each warp carries two samples and the kernel holds 16 warps per SM (128 registers).
+// The rollout is one wave of equally long CTAs, so its duration is set by the SM that received the most warps:
+// pick the warps-per-CTA w in 2..8 that minimises ceil(#CTAs / #SMs) * w, preferring large CTAs (their warps are
+// re-aligned every sub-step and share instruction-cache lines). K = 4096: w = 7 -> 2 CTAs = 14 warps on every SM
+// (w = 8 or 4 would put 16 on most SMs: +15 % time, measured).
+static int team_block(int K, int extra) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("M3P2I_TEAM_BLOCK");
+    forced = e ? atoi(e) : 0;
+    if (forced % 32 || forced < 32 || forced > kTeamBlockMax) forced = 0;
+  }
+  if (forced) return forced;
+  int best_w = 2, best_load = 1 << 30;
+  for (int w = 2; w <= kTeamBlockMax / 32; ++w) {
+    const int ctas = (K + 2 * w - 1) / (2 * w) + extra;
+    const int load = ((ctas + sms - 1) / sms) * w;
+    if (load <= best_load) { best_load = load; best_w = w; }
+  }
+  return 32 * best_w;
+}
+
 void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp,
                     const RolloutBufs& b, bool need_refs, cudaStream_t st, int* launches) {
   const int block = rollout_block(c.K);
@@ -238,8 +266,9 @@ void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, co
   if (env_type == M3P2I_ENV_POINT) {
     k_rollout<M3P2I_ENV_POINT><<<grid, block, 0, st>>>(c, *pp, b);
   } else if (c.lanes == kTeam) {
-    const int teams_per_block = kTeamBlock / kTeam;
-    k_rollout_team<<<(c.K + teams_per_block - 1) / teams_per_block + extra, kTeamBlock, 0, st>>>(c, *qp, b);
+    const int tb = team_block(c.K, extra);
+    const int teams_per_block = tb / kTeam;
+    k_rollout_team<<<(c.K + teams_per_block - 1) / teams_per_block + extra, tb, 0, st>>>(c, *qp, b);
   } else {
     k_rollout<M3P2I_ENV_PANDA><<<grid, block, 0, st>>>(c, *qp, b);
   }
