@@ -9,7 +9,7 @@
 namespace m3 {
 
 constexpr int kRolloutBlock = 32;
-constexpr int kTeamBlockMax = 256;  // team kernel: up to 8 warps (16 samples) per CTA, size chosen per launch (team_block)
+constexpr int kTeamBlockMax = 224;  // team kernel: up to 7 warps (14 samples) per CTA, size chosen per launch (team_block)
 constexpr int kStatsBlock = 1024;
 constexpr int kSumBlock = 256;
 
@@ -232,7 +232,7 @@ static int rollout_block(int K) {
 
 // CTA size of the team kernel. Each warp carries two samples and the kernel holds 16 warps per SM (128 registers).
 // The rollout is one wave of equally long CTAs, so its duration is set by the SM that received the most warps:
-// pick the warps-per-CTA w in 2..8 that minimises ceil(#CTAs / #SMs) * w, preferring large CTAs (their warps are
+// pick the warps-per-CTA w in 2..7 that minimises ceil(#CTAs / #SMs) * w, preferring large CTAs (their warps are
 // re-aligned every sub-step and share instruction-cache lines). K = 4096: w = 7 -> 2 CTAs = 14 warps on every SM
 // (w = 8 or 4 would put 16 on most SMs: +15 % time, measured).
 static int team_block(int K, int extra) {
