@@ -307,6 +307,7 @@ UpdateCfg make_ucfg(const H* h, int shift) {
   u.K = c.num_samples; u.T = c.horizon; u.nu = c.nu; u.Kg = c.num_samples_global; u.offset = c.sample_offset;
   u.multi_modal = c.multi_modal; u.env_type = c.env_type; u.filter_u = c.filter_u && h->have_filt; u.shift = shift;
   u.gamma = c.gamma; u.step_size_mean = c.step_size_mean;
+  u.fuse_finish = 0;
   return u;
 }
 
@@ -315,6 +316,7 @@ UpdateBufs make_ubufs(const H* h) {
   b.J_global = h->J_global.p; b.weights = h->weights.p; b.stats = h->stats.p; b.actions = h->actions.p;
   b.cost_sum = h->cost_sum.p; b.partials = h->partials.p; b.seq = h->seq.p; b.filt = h->have_filt ? h->filt.p : nullptr;
   b.cost_total = h->cost_total.p; b.result = h->result.p; b.info = h->info.p;
+  b.done_counter = h->ref_flags.p + 2;
   return b;
 }
 
@@ -361,8 +363,9 @@ int run_rollout(H* h, int* launches, const float* actions_in_dev) {
   return 0;
 }
 
-int run_update(H* h, int shift, int* launches) {
+int run_update(H* h, int shift, int* launches, bool fuse_finish = false) {
   UpdateCfg u = make_ucfg(h, shift);
+  u.fuse_finish = fuse_finish ? 1 : 0;
   UpdateBufs b = make_ubufs(h);
   launch_stats(u, b, h->stream, launches);
   launch_wsum(u, b, h->stream, launches);
@@ -432,9 +435,12 @@ int command_device(H* h) {
   CK(cudaEventRecord(h->evr, h->stream));
   h->have_evr = true;
   if ((rc = gather_J(h))) return rc;
-  if ((rc = run_update(h, 1, &launches))) return rc;
-  if ((rc = reduce_partials(h))) return rc;
-  if ((rc = run_finish(h, 1, &launches))) return rc;
+  const bool fused = h->nranks == 1 || !h->comm;   // no exchange between the sums and the mean update
+  if ((rc = run_update(h, 1, &launches, fused))) return rc;
+  if (!fused) {
+    if ((rc = reduce_partials(h))) return rc;
+    if ((rc = run_finish(h, 1, &launches))) return rc;
+  }
   CK(cudaEventRecord(h->ev1, h->stream));
   h->last_info.launches = launches;
   return 0;
@@ -523,7 +529,7 @@ int m3p2i_create(const M3P2IConfig* cfg, int device, m3p2i_handle* out) {
   if (e == cudaSuccess) e = h->cost_total.alloc(K);
   if (e == cudaSuccess) e = h->result.alloc(2 * TN);
   if (e == cudaSuccess) e = h->refs.alloc(T);
-  if (e == cudaSuccess) e = h->ref_flags.alloc(2);
+  if (e == cudaSuccess) e = h->ref_flags.alloc(4);   // [0,1] producer progress, [2] fused-update CTA counter
   if (e == cudaSuccess) e = h->stats.alloc(1);
   if (e == cudaSuccess) e = h->info.alloc(1);
   if (e == cudaSuccess) {

@@ -399,16 +399,19 @@ void launch_stats(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int*
 // CTA j < T*nu reduces plane j of the action buffer over this shard's K samples with the three weight sets
 // (mppi.py:498-499, m3p2i.py:80-86) and gathers the best rows (mppi.py:494-496, m3p2i.py:75-78);
 // CTA T*nu sums the undiscounted costs (the mean term of mppi.py:325).
+DEV void finish_body(const UpdateCfg& u, const UpdateBufs& b, float* smean);
+
 __global__ void __launch_bounds__(kSumBlock) k_wsum(const UpdateCfg u, const UpdateBufs b) {
+  extern __shared__ float smean[];  // [T*nu], used by the last CTA when the finish step is fused in
   __shared__ float sh[32];
+  __shared__ int is_last;
   const int K = u.K, Kg = u.Kg, half = Kg / 2, TN = u.T * u.nu, j = blockIdx.x;
   if (j == TN) {
     float a = 0.0f;
     for (int k = threadIdx.x; k < K; k += kSumBlock) a += b.cost_sum[k];
     a = block_sum<kSumBlock>(a, sh);
     if (threadIdx.x == 0) b.partials[6 * TN] = a;
-    return;
-  }
+  } else {
   const float* plane = b.actions + (size_t)j * K;
   const float* w0 = b.weights + u.offset;
   const float* w1 = b.weights + (size_t)Kg + u.offset;
@@ -436,10 +439,24 @@ __global__ void __launch_bounds__(kSumBlock) k_wsum(const UpdateCfg u, const Upd
       b.partials[(3 + s) * TN + j] = row;
     }
   }
+  }
+  if (!u.fuse_finish) return;
+  // single-GPU path: the CTA that finishes last applies the mean update (k_finish's work) in the same launch
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(b.done_counter, 1u);
+    is_last = done == gridDim.x - 1;
+    if (is_last) *b.done_counter = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  finish_body(u, b, smean);
 }
 
 void launch_wsum(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches) {
-  k_wsum<<<u.T * u.nu + 1, kSumBlock, 0, st>>>(u, b);
+  k_wsum<<<u.T * u.nu + 1, kSumBlock, sizeof(float) * u.T * u.nu, st>>>(u, b);
   ++*launches;
 }
 
@@ -447,11 +464,10 @@ void launch_wsum(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* 
 // mppi.py:494-503 / m3p2i.py:75-87 on the (all-reduced) partial sums; the one-step shift of the stored mean
 // (mppi.py:237,266-273) is folded in; Savitzky-Golay as a [T,T] matrix (mppi.py:257-263); cost_total aliasing
 // quirk cost_total = sum_t c + mean_k(sum_t c) (mppi.py:282-284,325).
-__global__ void __launch_bounds__(kSumBlock) k_finish(const UpdateCfg u, const UpdateBufs b) {
-  extern __shared__ float smean[];  // [T*nu] new mean
+DEV void finish_body(const UpdateCfg& u, const UpdateBufs& b, float* smean /* shared, [T*nu] */) {
   const int T = u.T, nu = u.nu, TN = T * nu;
   const float a2 = u.step_size_mean, a1 = (float)(1.0 - (double)u.step_size_mean);
-  const float* part = b.partials;
+  const volatile float* part = b.partials;   // written by other CTAs in the fused launch
   float* seq = b.seq;
   for (int i = threadIdx.x; i < TN; i += kSumBlock) {
     const int t = i / nu, d = i - t * nu;
@@ -493,6 +509,11 @@ __global__ void __launch_bounds__(kSumBlock) k_finish(const UpdateCfg u, const U
     in->mean_cost_sum = mean_cost;
     in->beta_iters = S->beta_iters;
   }
+}
+
+__global__ void __launch_bounds__(kSumBlock) k_finish(const UpdateCfg u, const UpdateBufs b) {
+  extern __shared__ float smean[];  // [T*nu] new mean
+  finish_body(u, b, smean);
 }
 
 void launch_finish(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches) {

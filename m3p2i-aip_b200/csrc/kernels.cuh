@@ -6,6 +6,7 @@ namespace m3 {
 
 struct UpdateCfg {
   int K, T, nu, Kg, offset, multi_modal, env_type, filter_u, shift;
+  int fuse_finish;   // k_wsum's last CTA also runs the finish step (no exchange between them: single rank)
   float gamma, step_size_mean;
 };
 
@@ -34,6 +35,7 @@ struct UpdateBufs {
   float* cost_total;       // [K]
   float* result;           // [T*nu] filtered action, followed by [T*nu] unfiltered mean
   M3P2ICommandInfo* info;  // device copy
+  unsigned* done_counter;  // CTA completion counter of the fused wsum + finish launch
 };
 
 void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp,
