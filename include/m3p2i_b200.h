@@ -265,6 +265,12 @@ int m3p2i_fetch_result(m3p2i_handle h, float* out_action, float* out_cost_total)
  * (either may be NULL). No planner state is touched. Used by the parity tests. */
 int m3p2i_rollout_actions(m3p2i_handle h, const float* actions, float* out_states, float* out_cost_horizon);
 
+/* Generic callback path, first half (mppi.py:237-242,381-416): applies the one-step shift to the stored sequences and
+ * writes this tick's perturbed action sequences out_actions [K_local,T,nu] (before u_scale), exactly the rows the
+ * fused command would roll out. The caller then runs its own dynamics / cost callbacks T times and finishes the
+ * tick with m3p2i_update_only. */
+int m3p2i_sample_actions(m3p2i_handle h, float* out_actions);
+
 /* Update on caller-supplied arrays: cost_horizon [K_local,T], actions [K_local,T,nu] (generic callback path,
  * mppi.py:327-331). out_action [T,nu] is the new mean_action (unfiltered). */
 int m3p2i_update_only(m3p2i_handle h, const float* cost_horizon, const float* actions,

@@ -777,6 +777,28 @@ int m3p2i_rollout_actions(m3p2i_handle h, const float* actions, float* out_state
   return 0;
 }
 
+int m3p2i_sample_actions(m3p2i_handle h, float* out_actions) {
+  if (!h || !out_actions) return fail(M3P2I_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  const size_t K = h->cfg.num_samples, TN = (size_t)h->cfg.horizon * h->cfg.nu;
+  if (h->cfg.noise_mode == M3P2I_NOISE_TABLE && !h->have_noise)
+    return fail(M3P2I_ERR_STATE, "table noise mode: m3p2i_set_noise_table has not been called");
+  CK(h->scratch.alloc(2 * K * TN));
+  RolloutCfg c = make_rcfg(h);
+  RolloutBufs b = make_rbufs(h);
+  c.preshifted = 1;
+  const float us = c.u_scale;
+  c.u_scale = 1.0f;       // perturbed_action is stored before u_scale is applied (mppi.py:297,411)
+  c.null_action = 0;      // the null action is applied inside the T-loop of the caller (mppi.py:300-302)
+  launch_sample_actions(h->cfg.env_type, c, b, h->seq.p, h->scratch.p, h->stream);
+  launch_transpose(h->scratch.p, h->scratch.p + K * TN, (int)TN, (int)K, h->stream);   // -> [K][T*nu]
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_actions, h->scratch.p + K * TN, sizeof(float) * K * TN, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  (void)us;
+  return 0;
+}
+
 int m3p2i_update_only(m3p2i_handle h, const float* cost_h, const float* actions, float* out_mean, M3P2ICommandInfo* info) {
   if (!h || !cost_h || !actions) return fail(M3P2I_ERR_ARG, "null argument");
   if (h->cfg.num_samples != h->cfg.num_samples_global) return fail(M3P2I_ERR_STATE, "update_only needs an unsharded handle");

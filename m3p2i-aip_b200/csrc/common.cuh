@@ -55,6 +55,7 @@ struct RolloutCfg {
   int task, gripper;
   int env_live;     // 1: start from the persistent env buffer, 0: from the broadcast base state
   int store_env;    // write the end state (and last velocity target) back to the env buffer
+  int preshifted;   // the stored sequences were already shifted (m3p2i_sample_actions): read them at t, not t+1
   int open_loop;    // actions are supplied (m3p2i_rollout_actions) instead of sampled
   unsigned epoch;   // ref_flags reach epoch + t + 1 when step t of this launch has been published
   int lanes;        // lanes per sample: 1 = one thread per sample, 16 = lane-cooperative team (panda_env)

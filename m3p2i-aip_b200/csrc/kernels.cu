@@ -40,7 +40,7 @@ DEV float env_cost(PandaEnv& e, const PandaParams& P, const RolloutCfg& c, int k
 template <int NU>
 DEV void perturb_action(const RolloutCfg& c, const RolloutBufs& b, int kg, int t, const float* delta_in, float* u) {
   const int TN = c.T * NU, half = c.Kg / 2;
-  const int ts = min(t + 1, c.T - 1);
+  const int ts = c.preshifted ? t : min(t + 1, c.T - 1);
   const float* mean = b.seq + (c.multi_modal ? (kg < half ? SEQ_MEAN1 : SEQ_MEAN2) : SEQ_MEAN) * TN + ts * NU;
 #pragma unroll
   for (int d = 0; d < NU; ++d) {
@@ -70,7 +70,7 @@ DEV void sample_action(const RolloutCfg& c, const RolloutBufs& b, int kg, int kl
 #pragma unroll
     for (int d = 0; d < NU; ++d) u[d] = c.u_scale * b.actions_in[(size_t)(t * NU + d) * K + kl];
   } else {
-    const int ts = min(t + 1, c.T - 1);
+    const int ts = c.preshifted ? t : min(t + 1, c.T - 1);
     const float* mean = b.seq + (c.multi_modal ? (kg < half ? SEQ_MEAN1 : SEQ_MEAN2) : SEQ_MEAN) * TN + ts * NU;
     float z[4];
 #pragma unroll
@@ -519,6 +519,43 @@ __global__ void __launch_bounds__(kSumBlock) k_finish(const UpdateCfg u, const U
 void launch_finish(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches) {
   k_finish<<<1, kSumBlock, sizeof(float) * u.T * u.nu, st>>>(u, b);
   ++*launches;
+}
+
+// ------------------------------------------------------------------ generic callback path: shift + sample only
+// MPPI._shift_action applied in place to the stored sequences (mppi.py:237-242,266-273)
+__global__ void k_shift_seq(float* seq, int T, int nu, int multi_modal) {
+  extern __shared__ float tmp[];
+  const int TN = T * nu;
+  for (int q = 0; q < SEQ_COUNT; ++q) {
+    const bool on = q == SEQ_MEAN || (multi_modal && (q == SEQ_MEAN1 || q == SEQ_MEAN2 || q == SEQ_BEST1 || q == SEQ_BEST2));
+    if (!on) continue;
+    for (int i = threadIdx.x; i < TN; i += blockDim.x) {
+      const int t = i / nu, d = i - t * nu;
+      tmp[i] = seq[q * TN + min(t + 1, T - 1) * nu + d];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TN; i += blockDim.x) seq[q * TN + i] = tmp[i];
+    __syncthreads();
+  }
+}
+
+template <int NU>
+__global__ void k_sample_actions(const __grid_constant__ RolloutCfg c, const RolloutBufs b, float* out /*[T][NU][K]*/) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= c.K) return;
+  float u[NU];
+  for (int t = 0; t < c.T; ++t) {
+    sample_action<NU>(c, b, c.offset + k, k, t, u);
+#pragma unroll
+    for (int d = 0; d < NU; ++d) out[(size_t)(t * NU + d) * c.K + k] = u[d];
+  }
+}
+
+void launch_sample_actions(int env_type, const RolloutCfg& c, const RolloutBufs& b, float* seq, float* out, cudaStream_t st) {
+  k_shift_seq<<<1, 256, sizeof(float) * c.T * c.nu, st>>>(seq, c.T, c.nu, c.multi_modal);
+  const int grid = (c.K + 127) / 128;
+  if (env_type == M3P2I_ENV_POINT) k_sample_actions<2><<<grid, 128, 0, st>>>(c, b, out);
+  else k_sample_actions<9><<<grid, 128, 0, st>>>(c, b, out);
 }
 
 __global__ void k_discount(const float* cost_h, float* J, float* cost_sum, int K, int T, float gamma) {

@@ -47,6 +47,9 @@ void launch_finish(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int
 void launch_discount(const float* cost_h, float* J, float* cost_sum, int K, int T, float gamma, cudaStream_t st,
                      int* launches);
 
+// shift the stored sequences in place, then write the perturbed actions of this tick (pre-u_scale) to out [T][nu][K]
+void launch_sample_actions(int env_type, const RolloutCfg& c, const RolloutBufs& b, float* seq, float* out, cudaStream_t st);
+
 void launch_sim_reset(int env_type, const float* base, float* env, int K, cudaStream_t st);
 void launch_sim_step(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp, float* env,
                      const float* vel_target, cudaStream_t st);

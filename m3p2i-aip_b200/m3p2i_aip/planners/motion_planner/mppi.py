@@ -123,6 +123,8 @@ class MPPI():
                 sim.attach_planner(cfg, noise_mode=A.NOISE_TABLE, seed=self.seed_val)
             scene = S.build_point_scene() if self.env_type == "point_env" else S.build_panda_scene()
             self.backend = native.NativePlanner(S.build_config(cfg, noise_mode=noise_mode, seed=self.seed_val), scene)
+            if self.filter_u:
+                self.backend.set_filter_matrix(S.savgol_matrix(self.T))
             # the softmin/update kernels need no scene state, but the handle wants one
             actors = S.default_actors(self.env_type)
             self.backend.set_state(S.initial_dof_state(actors), S.initial_root_state(actors))
@@ -202,11 +204,6 @@ class MPPI():
     def _running_cost(self, state):
         return self.running_cost(state)
 
-    def _shift_action(self, seq):
-        out = torch.roll(seq, -1, dims=0)
-        out[-1] = seq[-1]
-        return out
-
     def _rollout_callbacks(self, act):
         """The reference's T-step loop over the user's callbacks (mppi.py:296-315): -> cost_horizon, states, actions"""
         K, T = self.K, self.T
@@ -258,42 +255,19 @@ class MPPI():
         return action, info
 
     def _command_generic(self):
-        """mppi.py:237-245,381-416,275-332 with the user's callbacks; update through the native library."""
-        K, T, nu = self.K, self.T, self.nu
-        st = self.backend.get_planner_state()
-        seqs = {k: torch.from_numpy(np.asarray(getattr(st, k)[: T * nu], np.float32).reshape(T, nu).copy()) for k in _SEQ_KEYS}
-        seqs["mean_action"] = self._shift_action(seqs["mean_action"])
-        if self.multi_modal:
-            for k in ("mean_action_1", "mean_action_2", "best_traj_1", "best_traj_2"):
-                seqs[k] = self._shift_action(seqs[k])
-        delta = self._delta if torch.is_tensor(self._delta) else torch.from_numpy(self.backend.get_noise())
-        delta = delta.to(torch.float32).clone()
-        delta[-1] = 0.0
-        scaled = delta * torch.sqrt(torch.diagonal(self.noise_sigma))
-        if self.multi_modal:
-            act = torch.cat((seqs["mean_action_1"] + scaled[:self.half_K], seqs["mean_action_2"] + scaled[self.half_K:]), 0)
-        else:
-            act = seqs["mean_action"] + scaled
-        u_min = torch.tensor(list(self.backend.cfg.u_min)[:nu])
-        u_max = torch.tensor(list(self.backend.cfg.u_max)[:nu])
-        act = torch.max(torch.min(act, u_max), u_min)
-        if self.multi_modal:
-            act[0] = seqs["best_traj_1"]
-            act[self.half_K] = seqs["best_traj_2"]
-        if self.env_type == "panda_env" and self.gripper_command in ("open", "close"):
-            act[:, :, 7:9] = 1.5 if self.gripper_command == "open" else -1.5
+        """The reference's control flow with the user's callbacks (mppi.py:237-245,381-416,275-332): shift and
+        perturbation (m3p2i_sample_actions), T callback steps, softmin / mean update / filter (m3p2i_update_only)."""
+        grip = self.gripper_command if self.env_type == "panda_env" else None
+        self.backend.set_objective("reach" if self.env_type == "panda_env" else "navigation",
+                                   np.zeros(7 if self.env_type == "panda_env" else 2, np.float32), grip)
+        act = torch.from_numpy(self.backend.sample_actions())
         cost_horizon, states, actions = self._rollout_callbacks(act)
         self._lazy["states"] = states
-        for k in _SEQ_KEYS:
-            getattr(st, k)[: T * nu] = seqs[k].reshape(-1).tolist()
-        self.backend.set_planner_state(st)
-        mean, info = self.backend.update_only(cost_horizon.numpy(), actions.numpy())
+        _, info = self.backend.update_only(cost_horizon.numpy(), actions.numpy())
         cs = cost_horizon.sum(1)
         self._lazy["cost_total"] = cs + cs.mean()
         self._lazy["actions"] = actions / self.u_scale
-        action = mean
-        if self.filter_u:
-            action = S.savgol_matrix(T) @ mean
+        action = np.array(self.backend.fetch_result(want_cost=False)[0], copy=True)   # filtered when filter_u
         return action, info
 
     # ------------------------------------------------------------------ results of the last command (read lazily)

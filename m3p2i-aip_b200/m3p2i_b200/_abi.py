@@ -116,6 +116,7 @@ PROTOTYPES = {
     "m3p2i_command_resident": (C.c_int, [vp, C.POINTER(CommandInfo)]),
     "m3p2i_fetch_result": (C.c_int, [vp, fp, fp]),
     "m3p2i_rollout_actions": (C.c_int, [vp, fp, fp, fp]),
+    "m3p2i_sample_actions": (C.c_int, [vp, fp]),
     "m3p2i_update_only": (C.c_int, [vp, fp, fp, fp, C.POINTER(CommandInfo)]),
     "m3p2i_top_trajs": (C.c_int, [vp, C.c_int, ip, fp, fp]),
     "m3p2i_get_buffer": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]),

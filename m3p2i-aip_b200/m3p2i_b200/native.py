@@ -157,6 +157,12 @@ class NativePlanner:
         self._ck(self.fn["m3p2i_rollout_actions"](self.h, A.as_fp(a), A.as_fp(st), A.as_fp(ch)), "m3p2i_rollout_actions")
         return st, ch
 
+    def sample_actions(self):
+        """Shift the stored sequences and return this tick's perturbed actions [K,T,nu] (generic callback path)."""
+        out = np.empty((self.K, self.T, self.nu), np.float32)
+        self._ck(self.fn["m3p2i_sample_actions"](self.h, A.as_fp(out)), "m3p2i_sample_actions")
+        return out
+
     def update_only(self, cost_horizon, actions):
         ch, a = _f32(cost_horizon), _f32(actions)
         if ch.shape != (self.K, self.T) or a.shape != (self.K, self.T, self.nu):
