@@ -120,6 +120,63 @@ DEV V3 apply_hits(bool hit, V3 n, float depth, V3 p, int src0, bool mine, Solve&
   return acc;
 }
 
+// One own-corner / fixed-box contact as the lane that found it describes it. Positions do not move inside a
+// sub-step, so everything that depends on geometry only (lever arm ra, ra x n, 1 / normal effective mass, target
+// normal speed) is worked out ONCE, by all corner lanes in parallel, and only the velocity-dependent part of
+// solve_cube_static is left in the serial Gauss-Seidel chain.
+struct StaticHit {
+  bool hit;
+  V3 n, rn;
+  float ikn, target;
+};
+
+DEV StaticHit static_hit(bool near, V3 pc, V3 ra, const OBox3& sb, float im, float ii, float inv_h, const PandaParams& P) {
+  StaticHit s;
+  s.n = mk(0, 0, 0);
+  float depth = 0.0f;
+  s.hit = near && point_in_box(pc, sb, P.contact_margin, s.n, depth);
+  s.rn = cross(ra, s.n);
+  s.ikn = __fdividef(1.0f, im + ii * dot(s.rn, s.rn));
+  s.target = depth > 0.0f ? fminf(P.baumgarte * fmaxf(depth - P.slop, 0.0f) * inv_h, P.max_corr_vel) : depth * inv_h;
+  return s;
+}
+
+// Serial application (ascending corner order, as apply_hits) of the fixed-box contacts of the own cube: the same
+// equations as solve_cube_static with the geometry terms taken from the StaticHit of the lane that found the contact.
+DEV V3 apply_static_hits(const StaticHit& s, V3 ra, int group_base, V3& v, V3& w, float im, float ii, float mu) {
+  const unsigned hb = __ballot_sync(kFull, s.hit);
+  V3 acc = mk(0, 0, 0);
+  unsigned todo = (hb | (hb >> 8) | (hb >> 16) | (hb >> 24)) & 0xffu;
+  while (todo) {
+    const int j = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int src = group_base + j;
+    const V3 n = shfl3(s.n, src), rn = shfl3(s.rn, src), r = shfl3(ra, src);
+    const float ikn = __shfl_sync(kFull, s.ikn, src), target = __shfl_sync(kFull, s.target, src);
+    const float jn = (target - (dot(v, n) + dot(w, rn))) * ikn;
+    if (((hb >> src) & 1u) && jn > 0.0f) {
+      v = v + (jn * im) * n;
+      w = w + (jn * ii) * rn;
+      const V3 va = v + cross(w, r);
+      const float vn = dot(va, n);
+      V3 t = va - vn * n;
+      const float vt2 = dot(t, t);
+      acc = acc + jn * n;
+      if (vt2 >= 1e-18f) {
+        const float ivt = rsqrtf(vt2), vt = vt2 * ivt;
+        t = ivt * t;
+        const V3 rt = cross(r, t);
+        const float kt = im + ii * dot(rt, rt);
+        const float jt = fminf(__fdividef(vt, kt), mu * jn);
+        v = v - (jt * im) * t;
+        w = w - (jt * ii) * rt;
+        acc = acc - jt * t;
+      }
+    }
+  }
+  return acc;
+}
+
 // hand pose + twist; sin/cos of joint j are computed by lane j of the team (one sincosf site) and broadcast
 DEV void team_fk(const PandaParams& P, const float* q, const float* qd, const TeamLane& t, Hand& H) {
   const int j = min(t.lane & 15, 6);
@@ -307,6 +364,12 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       if (boxes_near(lb, cb, P.contact_margin)) lnear |= 1u << f;
     }
 
+    // geometry-only part of the own corner's fixed-box contacts (see StaticHit)
+    const V3 ra = pc - x;
+    const float inv_h = __frcp_rn(h);
+    const int ks0 = near_any ? __ffs(near_any) - 1 : 0;
+    const StaticHit sh0 = static_hit(near_any && ((near_mask >> ks0) & 1u), pc, ra, obox_of(P.st[ks0]), im, ii, inv_h, P);
+
 #pragma unroll 1
     for (int p = 0; p < c.passes; ++p) {
       // (a) own cube against the fixed boxes
@@ -315,13 +378,10 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
         const int ks = __ffs(todo_k) - 1;
         const OBox3 sb = obox_of(P.st[ks]);
         const bool near = (near_mask >> ks) & 1u;
-        V3 n = mk(0, 0, 0);
-        float depth = 0.0f;
-        const bool hit = near && point_in_box(pc, sb, P.contact_margin, n, depth);
+        // the first near box (almost always the only one: the table) was tested before the pass loop
+        const StaticHit sh = ks == ks0 ? sh0 : static_hit(near, pc, ra, sb, im, ii, inv_h, P);
         const float mu = 0.5f * (mu_c + P.st[ks].mu);
-        const V3 got = apply_hits(hit, n, depth, pc, t.group_base, true, [&](V3 nj, float dj, V3 pj) {
-          return solve_cube_static(v, w, im, ii, x, nj, dj, pj, mu, h, P);
-        });
+        const V3 got = apply_static_hits(sh, ra, t.group_base, v, w, im, ii, mu);
         // impulses received by the fixed box = -(impulses on the cube)
         if (ks == P.idx_table) imp_table = imp_table - got;
         if (ks == P.idx_shelf) imp_shelf = imp_shelf - got;
