@@ -177,6 +177,69 @@ DEV V3 apply_static_hits(const StaticHit& s, V3 ra, int group_base, V3& v, V3& w
   return acc;
 }
 
+// The same split for a kinematic link (prescribed twist; a finger adds one sliding DoF) against the own cube:
+// geometry and the link's prescribed point velocity per contact in parallel, velocity part serial. Normal `n` points
+// from the cube to the link (solve_link_cube's convention).
+struct LinkHit {
+  bool hit;
+  V3 n, rcn, rc, vl0;
+  float an, ikn, target;
+};
+
+DEV LinkHit link_hit(bool hit, V3 n, float depth, V3 pt, const Hand& H, V3 axis, float ims, V3 x, float im, float ii,
+                     float inv_h, const PandaParams& P) {
+  LinkHit s;
+  s.hit = hit; s.n = n;
+  s.rc = pt - x;
+  s.vl0 = H.v + cross(H.w, pt - H.p);
+  s.rcn = cross(s.rc, n);
+  s.an = dot(axis, n);
+  s.ikn = __fdividef(1.0f, ims * s.an * s.an + im + ii * dot(s.rcn, s.rcn));
+  s.target = depth > 0.0f ? fminf(P.baumgarte * fmaxf(depth - P.slop, 0.0f) * inv_h, P.max_corr_vel) : depth * inv_h;
+  return s;
+}
+
+// Serial application of the link contacts found by lanes [src0, src0+8); returns the sum of the impulses on the link.
+DEV V3 apply_link_hits(const LinkHit& s, int src0, bool mine, V3 axis, float& slide, float ims, V3& v, V3& w, float im,
+                       float ii, float mu) {
+  const unsigned hb = __ballot_sync(kFull, s.hit);
+  V3 acc = mk(0, 0, 0);
+  unsigned todo = (hb | (hb >> 8) | (hb >> 16) | (hb >> 24)) & 0xffu;
+  while (todo) {
+    const int j = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int src = src0 + j;
+    const V3 n = shfl3(s.n, src), rcn = shfl3(s.rcn, src), rc = shfl3(s.rc, src), vl0 = shfl3(s.vl0, src);
+    const float an = __shfl_sync(kFull, s.an, src), ikn = __shfl_sync(kFull, s.ikn, src);
+    const float target = __shfl_sync(kFull, s.target, src);
+    const float vn0 = dot(vl0, n) + slide * an - (dot(v, n) + dot(w, rcn));
+    const float jn = (target - vn0) * ikn;
+    if (mine && ((hb >> src) & 1u) && jn > 0.0f) {
+      slide += ims * an * jn;
+      v = v - (jn * im) * n;
+      w = w - (jn * ii) * rcn;
+      const V3 rv = (vl0 + slide * axis) - (v + cross(w, rc));
+      const float vn = dot(rv, n);
+      V3 t = rv - vn * n;
+      const float vt2 = dot(t, t);
+      acc = acc + jn * n;
+      if (vt2 >= 1e-18f) {
+        const float ivt = rsqrtf(vt2), vt = vt2 * ivt;
+        t = ivt * t;
+        const V3 rct = cross(rc, t);
+        const float at = dot(axis, t);
+        const float kt = ims * at * at + im + ii * dot(rct, rct);
+        const float jt = fminf(__fdividef(vt, kt), mu * jn);
+        slide -= ims * at * jt;
+        v = v + (jt * im) * t;
+        w = w + (jt * ii) * rct;
+        acc = acc - jt * t;
+      }
+    }
+  }
+  return acc;
+}
+
 // hand pose + twist; sin/cos of joint j are computed by lane j of the team (one sincosf site) and broadcast
 DEV void team_fk(const PandaParams& P, const float* q, const float* qd, const TeamLane& t, Hand& H) {
   const int j = min(t.lane & 15, 6);
@@ -328,6 +391,10 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     float slide[2] = {e.qd[7], e.qd[8]};
     OBox3 cb;  // own cube
     cb.c = e.cu.p; cb.R = quat_to_R(e.cu.qx, e.cu.qy, e.cu.qz, e.cu.qw); cb.half = half_own;
+    // keep the nine entries as values: under register pressure ptxas otherwise re-derives them from the quaternion
+    // inside the contact loops (26 instructions per use, 12 % of all instructions in a grasp state)
+    asm volatile("" : "+f"(cb.R.cx.x), "+f"(cb.R.cx.y), "+f"(cb.R.cx.z), "+f"(cb.R.cy.x), "+f"(cb.R.cy.y), "+f"(cb.R.cy.z),
+                      "+f"(cb.R.cz.x), "+f"(cb.R.cz.y), "+f"(cb.R.cz.z));
     const V3 pc = box_corner(cb, t.c);  // own corner
     V3 v = e.cu.v, w = e.cu.w;
     const V3 x = e.cu.p;
@@ -440,9 +507,8 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
             float depth = 0.0f;
             const bool hit = mine && point_in_box(pt, bx, P.contact_margin, n, depth);
             const float sg = ph == 0 ? 1.0f : -1.0f;
-            got = got + apply_hits(hit, n, depth, pt, t.team_base + 8 * i, mine, [&](V3 nj, float dj, V3 pj) {
-              return solve_link_cube(H.v, H.w, H.p, axis, sl_f, ims, v, w, im, ii, x, sg * nj, dj, pj, mu, h, P);
-            });
+            const LinkHit lh = link_hit(hit, sg * n, depth, pt, H, axis, ims, x, im, ii, inv_h, P);
+            got = got + apply_link_hits(lh, t.team_base + 8 * i, mine, axis, sl_f, ims, v, w, im, ii, mu);
           }
           if (mine && i == 1) imp_cubeb = imp_cubeb - got;
           // the finger's sliding speed is shared by both groups: take it from the group that worked the pair
