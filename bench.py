@@ -270,7 +270,8 @@ def main():
             flush.fill_(i & 1)
         info = planner.command_resident(sync=True)
         roll_ms.append(info.rollout_ms)
-    launches_per_step = planner.command_resident(sync=True).launches
+    last = planner.command_resident(sync=True)
+    launches_per_step, lanes = last.launches, int(last.rollout_lanes)
     barrier()
 
     # ---------------- end to end through the public API with host buffers (H2D state in, D2H action out)
@@ -311,7 +312,7 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_rollout_team (panda_env, 16 lanes per sample)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": (f"k_rollout_team (panda_env, {lanes} lanes per sample)" if lanes > 1 else "k_rollout<panda_env> (thread per sample)"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(), "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_ncu_rollout_team_summary.csv)",
                          "algorithmic_bytes_per_launch": B_ROLLOUT * K_PER_GPU * HORIZON, "peak_source": peak_src,
                          "bytes_per_sample_step": B_ROLLOUT, "kernel_ms": r_ms,

@@ -103,7 +103,7 @@ typedef struct M3P2IConfig {
   int32_t substeps;            /* IsaacGymConfig.substeps (isaacgym_wrapper.py:10) */
   int32_t solver_passes;       /* contact solver sweeps per substep (our integrator; default 2) */
   int32_t lanes_per_sample;    /* rollout kernel shape: 0 = library chooses, 1 = one thread per sample,
-                                  16 = lane-cooperative team of 16 lanes per sample (panda_env) */
+                                  8 / 16 = lane-cooperative team of that many lanes per sample (panda_env) */
   int32_t reserved_i[3];
   float dt;                    /* cfg.isaacgym.dt */
   float gamma;                 /* cfg.mppi.rollout_var_discount (mppi.py:181) */
@@ -214,7 +214,7 @@ typedef struct M3P2ICommandInfo {
   int32_t launches;   /* kernels launched by this command */
   int32_t beta_iters; /* iterations of the on-the-fly beta search (m3p2i.py:30-43), summed over sets */
   float rollout_ms;   /* device time of the fused rollout kernel alone (the roofline figure is computed from it) */
-  float reserved;
+  int32_t rollout_lanes; /* lanes per sample of the rollout kernel this command used (1, 8 or 16) */
 } M3P2ICommandInfo;
 
 typedef struct M3P2IHandle_* m3p2i_handle;

@@ -84,6 +84,7 @@ struct DevBuf {
 struct M3P2IHandle_ {
   M3P2IConfig cfg;
   int device = 0;
+  int sm_count = 0;   // multiprocessors of `device` (the rollout kernel shape is chosen against it)
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr = nullptr;
   bool have_scene = false, have_state = false, env_live = false, env_alloc = false, base_dirty = false;
@@ -257,9 +258,14 @@ int materialize(H* h) {
   return 0;
 }
 
-// lanes per sample of the rollout kernel: the lane-cooperative team kernel shortens the per-sample serial chain and
-// wins while the GPU is not full (16 * K threads <= ~1 resident wave); beyond that the redundant work of a team
-// costs more than it hides. cfg.lanes_per_sample: 0 = choose, 1 = thread per sample, 16 = team.
+// lanes per sample of the rollout kernel: the lane-cooperative team kernels shorten the per-sample serial chain and
+// win while the GPU is not full; beyond that the redundant work of a team costs more than it hides.
+// cfg.lanes_per_sample: 0 = choose, 1 = thread per sample, 8 / 16 = team of that size.
+// Measured on B200 (profiles/r01_ksweep_lanes_v3.csv), 148 SMs, CTAs of 7 warps:
+//   K <= 14 * SMs (2072): 16 lanes, one CTA per SM, full register file (no spills)     0.31 - 0.35 ms
+//   K <= 28 * SMs (4144):  8 lanes, one CTA per SM, full register file                 0.36 - 0.39 ms
+//   K <= 56 * SMs (8288):  8 lanes, two CTAs per SM (128 registers)                    0.51 - 0.61 ms
+//   larger K: one thread per sample (flat 0.99 ms up to K = 16384, then throughput-bound)
 int rollout_lanes(const H* h) {
   if (h->cfg.env_type != M3P2I_ENV_PANDA) return 1;
   static int forced = -1;
@@ -268,8 +274,11 @@ int rollout_lanes(const H* h) {
     forced = e ? atoi(e) : 0;
   }
   int want = forced ? forced : h->cfg.lanes_per_sample;
-  if (want == 1 || want == 16) return want;
-  return h->cfg.num_samples <= 4608 ? 16 : 1;   // measured crossover on B200 (profiles/r01_ksweep_lanes.csv)
+  if (want == 1 || want == 8 || want == 16) return want;
+  const int sms = h->sm_count > 0 ? h->sm_count : 148;
+  if (h->cfg.num_samples <= 14 * sms) return 16;
+  if (h->cfg.num_samples <= 56 * sms) return 8;
+  return 1;
 }
 
 RolloutCfg make_rcfg(const H* h) {
@@ -422,6 +431,7 @@ int fetch(H* h, float* out_action, float* out_cost_total, M3P2ICommandInfo* info
   h->last_info.kernel_ms = kms;
   h->last_info.rollout_ms = rms;
   h->last_info.launches = nl;
+  h->last_info.rollout_lanes = rollout_lanes(h);
   if (info) *info = h->last_info;
   return 0;
 }
@@ -450,6 +460,7 @@ int finish_timing(H* h) {
   float ms = 0.0f;
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_info.kernel_ms = ms;
+  h->last_info.rollout_lanes = rollout_lanes(h);
   h->last_info.rollout_ms = 0.0f;
   if (h->have_evr) {
     CK(cudaEventElapsedTime(&ms, h->ev0, h->evr));
@@ -508,6 +519,7 @@ int m3p2i_create(const M3P2IConfig* cfg, int device, m3p2i_handle* out) {
     return fail(M3P2I_ERR_ARG, "sample_offset + num_samples exceeds num_samples_global");
   }
   h->device = device;
+  if (cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) h->sm_count = 0;
   h->ndof = ndof_of(h); h->nf = nf_of(h);
   h->task = c.env_type == M3P2I_ENV_POINT ? M3P2I_TASK_NAVIGATION : M3P2I_TASK_REACH;
   const size_t K = c.num_samples, T = c.horizon, nu = c.nu, Kg = c.num_samples_global, TN = T * nu;

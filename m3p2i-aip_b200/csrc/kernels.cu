@@ -198,15 +198,17 @@ k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename
 
 namespace m3 {
 
-// Lane-cooperative variant for panda_env: 16 lanes per sample (panda_team.cuh), two samples per warp.
+// Lane-cooperative variant for panda_env: 16 / CPL lanes per sample (panda_team.cuh), 2 * CPL samples per warp.
 // CTA 0 is the producer of the batch rows read by the reach cost when b.refs is set.
-__global__ void __launch_bounds__(kTeamBlockMax, 2)
+template <int CPL, int MINB>
+__global__ void __launch_bounds__(kTeamBlockMax, MINB)
 k_rollout_team(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
-  const TeamLane t = team_lane();
+  constexpr int TM = TeamShape<CPL>::kTeam;
+  const TeamLane t = team_lane<CPL>();
   const bool use_refs = b.refs != nullptr;
   const bool producer = use_refs && blockIdx.x == 0;
-  const int which = t.lane >> 4;   // producer CTA: team 0 replays global row 0, team 1 global row Kg/2
-  const int kraw = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x + threadIdx.x) / kTeam;
+  const int which = t.lane / TM;   // producer CTA: team 0 replays global row 0, team 1 global row Kg/2
+  const int kraw = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x + threadIdx.x) / TM;
   const bool valid = !producer && kraw < c.K;
   int k = kraw < c.K ? kraw : c.K - 1;   // idle teams shadow the last sample so that every shuffle has 32 lanes
   int kg = c.offset + k;
@@ -214,7 +216,7 @@ k_rollout_team(const __grid_constant__ RolloutCfg c, const __grid_constant__ Pan
     kg = (which == 1 && c.multi_modal) ? c.Kg / 2 : 0;
     k = (kg >= c.offset && kg < c.offset + c.K) ? kg - c.offset : -1;
   }
-  team_rollout(c, P, b, t, k, kg, valid, producer, which);
+  team_rollout<CPL>(c, P, b, t, k, kg, valid, producer, which);
 }
 
 // Threads per CTA of the rollout kernel. The kernel is latency-bound (one serial chain per sample), so small CTAs
@@ -235,13 +237,18 @@ static int rollout_block(int K) {
 // pick the warps-per-CTA w in 2..7 that minimises ceil(#CTAs / #SMs) * w, preferring large CTAs (their warps are
 // re-aligned every sub-step and share instruction-cache lines). K = 4096: w = 7 -> 2 CTAs = 14 warps on every SM
 // (w = 8 or 4 would put 16 on most SMs: +15 % time, measured).
-static int team_block(int K, int extra) {
+static int team_sms() {
   static int sms = 0;
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
+  return sms;
+}
+
+static int team_block(int K, int extra, int per_warp) {
+  const int sms = team_sms();
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("M3P2I_TEAM_BLOCK");
@@ -251,7 +258,7 @@ static int team_block(int K, int extra) {
   if (forced) return forced;
   int best_w = 2, best_load = 1 << 30;
   for (int w = 2; w <= kTeamBlockMax / 32; ++w) {
-    const int ctas = (K + 2 * w - 1) / (2 * w) + extra;
+    const int ctas = (K + per_warp * w - 1) / (per_warp * w) + extra;
     const int load = ((ctas + sms - 1) / sms) * w;
     if (load <= best_load) { best_load = load; best_w = w; }
   }
@@ -265,10 +272,17 @@ void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, co
   const int grid = (c.K + block - 1) / block + extra;
   if (env_type == M3P2I_ENV_POINT) {
     k_rollout<M3P2I_ENV_POINT><<<grid, block, 0, st>>>(c, *pp, b);
-  } else if (c.lanes == kTeam) {
-    const int tb = team_block(c.K, extra);
-    const int teams_per_block = tb / kTeam;
-    k_rollout_team<<<(c.K + teams_per_block - 1) / teams_per_block + extra, tb, 0, st>>>(c, *qp, b);
+  } else if (c.lanes == 16 || c.lanes == 8) {
+    const int per_warp = 32 / c.lanes;
+    const int tb = team_block(c.K, extra, per_warp);
+    const int teams_per_block = tb / c.lanes;
+    const int tgrid = (c.K + teams_per_block - 1) / teams_per_block + extra;
+    // MINB = 1: the whole grid is one CTA per SM, so the kernel may use the full register file (no spills)
+    const bool one_wave = tgrid <= team_sms();
+    if (c.lanes == 16 && one_wave) k_rollout_team<1, 1><<<tgrid, tb, 0, st>>>(c, *qp, b);
+    else if (c.lanes == 16) k_rollout_team<1, 2><<<tgrid, tb, 0, st>>>(c, *qp, b);
+    else if (one_wave) k_rollout_team<2, 1><<<tgrid, tb, 0, st>>>(c, *qp, b);
+    else k_rollout_team<2, 2><<<tgrid, tb, 0, st>>>(c, *qp, b);
   } else {
     k_rollout<M3P2I_ENV_PANDA><<<grid, block, 0, st>>>(c, *qp, b);
   }

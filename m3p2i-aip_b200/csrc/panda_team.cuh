@@ -1,15 +1,18 @@
-// panda_team.cuh — lane-cooperative Panda rollout: a TEAM of 16 lanes advances ONE sample.
+// panda_team.cuh — lane-cooperative Panda rollout: a TEAM of lanes advances ONE sample.
 //
 // Why: at the sizes the planner runs at (K = 4096 samples) a thread-per-sample rollout is one warp per SM walking a
 // ~20 k-instruction serial chain per step, with 3/4 of the SM sub-partitions idle. The work inside a sample is mostly
 // contact detection (independent per box corner) and Gauss-Seidel impulse solves (serial per body, but the two cubes
-// are independent of each other). A team splits it like this:
-//     lane bit 3  (g) : which cube the lane works for (0 = cubeA, 1 = cubeB); each 8-lane group keeps a replica of
-//                       "its" cube's state and applies that cube's impulses in lock-step
-//     lane bits 0-2 (c): which box corner the lane tests
-// Joint state, forward kinematics and the link boxes are replicated in all 16 lanes (drives, sin/cos and the Philox
-// blocks are computed by one lane each and broadcast). Contact detection runs on all corners at once; the solves are
-// broadcast (warp shuffles) and applied in exactly the pair / corner order of the thread-per-sample code
+// are independent of each other). A team splits it like this (CPL = corners per lane, 1 or 2):
+//     group bit (g)   : which cube the lane works for (0 = cubeA, 1 = cubeB); each group of 8 / CPL lanes keeps a
+//                       replica of "its" cube's state and applies that cube's impulses in lock-step
+//     lane in group c : the lane tests box corners c, c + 8 / CPL, ... (CPL of them)
+// so a team is 16 / CPL lanes and a warp carries 2 * CPL samples. CPL = 1 has the shortest per-sample chain (best
+// while the GPU is far from full), CPL = 2 halves the number of warp-instructions per sample because the serial
+// solves, the forward kinematics and the cost are replicated over 8 instead of 16 lanes.
+// Joint state, forward kinematics and the link boxes are replicated in all lanes of a team (drives, sin/cos and the
+// Philox blocks are computed by one lane each and broadcast). Contact detection runs on all corners at once; the
+// solves are broadcast (warp shuffles) and applied in exactly the pair / corner order of the thread-per-sample code
 // (panda_env.cuh), so both produce the same trajectory up to fp32 rounding of reordered sums.
 // All branches that contain shuffles are warp-uniform (decided by __ballot_sync / __any_sync).
 //
@@ -17,33 +20,60 @@
 // is instruction-fetch bound as soon as its loop body outgrows the instruction cache (ncu: 75 % `no_inst` stalls with
 // the unrolled version in contact-rich states). Hence ONE copy of everything: one forward-kinematics site per
 // sub-step (the cost of step t is evaluated from the FK of the first sub-step of step t+1 — same joint positions),
-// link / cube pairs and the two detection directions as rolled loops, one inlined copy of each contact solve.
+// link / cube pairs, the two detection directions and the corner slots as rolled loops, one inlined copy of each
+// contact solve.
 #pragma once
 #include "panda_env.cuh"
 
 namespace m3 {
 
-constexpr int kTeam = 16;
 constexpr unsigned kFull = 0xffffffffu;
+
+template <int CPL>
+struct TeamShape {
+  static_assert(CPL == 1 || CPL == 2, "corners per lane: 1 (16-lane teams) or 2 (8-lane teams)");
+  static constexpr int kGroup = 8 / CPL;    // lanes per cube
+  static constexpr int kTeam = 16 / CPL;    // lanes per sample
+};
 
 DEV V3 shfl3(V3 a, int src) {
   return mk(__shfl_sync(kFull, a.x, src), __shfl_sync(kFull, a.y, src), __shfl_sync(kFull, a.z, src));
 }
 DEV V3 sel3(bool c, V3 a, V3 b) { return mk(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
 
+// corner i of box b relative to its centre (box_corner(b, i) == b.c + corner_arm(b, i))
+DEV V3 corner_arm(const OBox3& b, int i) {
+  return mul(b.R, mk((i & 1) ? b.half.x : -b.half.x, (i & 2) ? b.half.y : -b.half.y, (i & 4) ? b.half.z : -b.half.z));
+}
+
+// fold a warp ballot onto the lanes of one group: bit j = lane j of ANY group of the warp voted
+template <int G>
+DEV unsigned fold(unsigned hb) {
+  hb |= hb >> 16;
+  hb |= hb >> 8;
+  if (G <= 4) hb |= hb >> 4;
+  return hb & ((1u << G) - 1u);
+}
+
 struct TeamLane {
-  int lane, g, c;     // lane in warp, cube group, corner
+  int lane, g, c;     // lane in warp, cube group, lane in group (first corner)
+  int tl;             // lane in team
   int team_base;      // first lane of this team in the warp
-  int group_base;     // first lane of this 8-lane group in the warp
+  int group_base;     // first lane of this group in the warp
+  int other;          // the lane with the same corners in the other group of the team
 };
 
+template <int CPL>
 DEV TeamLane team_lane() {
+  constexpr int G = TeamShape<CPL>::kGroup, TM = TeamShape<CPL>::kTeam;
   TeamLane t;
   t.lane = threadIdx.x & 31;
-  t.g = (t.lane >> 3) & 1;
-  t.c = t.lane & 7;
-  t.team_base = t.lane & 16;
-  t.group_base = t.lane & 24;
+  t.g = (t.lane / G) & 1;
+  t.c = t.lane & (G - 1);
+  t.tl = t.lane & (TM - 1);
+  t.team_base = t.lane & ~(TM - 1);
+  t.group_base = t.lane & ~(G - 1);
+  t.other = t.lane ^ G;
   return t;
 }
 
@@ -99,15 +129,15 @@ DEV Dyn3 dyn_cube(V3 v, V3 w, V3 x, float im, float ii) {
   return d;
 }
 
-// Serial application of the contacts found by the lanes [src0, src0+8): for corner j = 0..7 in order, the lane that
-// found a hit broadcasts (n, depth, p) and every lane for which `mine` holds applies solve(n, depth, p).
+// Serial application of the contacts found by the G lanes [src0, src0+G): for lane j = 0..G-1 in order, the lane
+// that found a hit broadcasts (n, depth, p) and every lane for which `mine` holds applies solve(n, depth, p).
 // Returns the sum of the impulses the solves report. The loop bounds and the shuffles are warp-uniform.
-template <typename Solve>
+template <int G, typename Solve>
 DEV V3 apply_hits(bool hit, V3 n, float depth, V3 p, int src0, bool mine, Solve&& solve) {
   const unsigned hb = __ballot_sync(kFull, hit);
   V3 acc = mk(0, 0, 0);
-  // corners that hit in ANY 8-lane group of the warp, visited in ascending corner order
-  unsigned todo = (hb | (hb >> 8) | (hb >> 16) | (hb >> 24)) & 0xffu;
+  // lanes that hit in ANY group of the warp, visited in ascending order
+  unsigned todo = fold<G>(hb);
   while (todo) {
     const int j = __ffs(todo) - 1;
     todo &= todo - 1;
@@ -143,10 +173,11 @@ DEV StaticHit static_hit(bool near, V3 pc, V3 ra, const OBox3& sb, float im, flo
 
 // Serial application (ascending corner order, as apply_hits) of the fixed-box contacts of the own cube: the same
 // equations as solve_cube_static with the geometry terms taken from the StaticHit of the lane that found the contact.
+template <int G>
 DEV V3 apply_static_hits(const StaticHit& s, V3 ra, int group_base, V3& v, V3& w, float im, float ii, float mu) {
   const unsigned hb = __ballot_sync(kFull, s.hit);
   V3 acc = mk(0, 0, 0);
-  unsigned todo = (hb | (hb >> 8) | (hb >> 16) | (hb >> 24)) & 0xffu;
+  unsigned todo = fold<G>(hb);
   while (todo) {
     const int j = __ffs(todo) - 1;
     todo &= todo - 1;
@@ -186,12 +217,13 @@ struct LinkHit {
   float an, ikn, target;
 };
 
-DEV LinkHit link_hit(bool hit, V3 n, float depth, V3 pt, const Hand& H, V3 axis, float ims, V3 x, float im, float ii,
-                     float inv_h, const PandaParams& P) {
+struct Hand;
+DEV LinkHit link_hit(bool hit, V3 n, float depth, V3 pt, V3 hv, V3 hw, V3 hp, V3 axis, float ims, V3 x, float im,
+                     float ii, float inv_h, const PandaParams& P) {
   LinkHit s;
   s.hit = hit; s.n = n;
   s.rc = pt - x;
-  s.vl0 = H.v + cross(H.w, pt - H.p);
+  s.vl0 = hv + cross(hw, pt - hp);
   s.rcn = cross(s.rc, n);
   s.an = dot(axis, n);
   s.ikn = __fdividef(1.0f, ims * s.an * s.an + im + ii * dot(s.rcn, s.rcn));
@@ -199,12 +231,13 @@ DEV LinkHit link_hit(bool hit, V3 n, float depth, V3 pt, const Hand& H, V3 axis,
   return s;
 }
 
-// Serial application of the link contacts found by lanes [src0, src0+8); returns the sum of the impulses on the link.
+// Serial application of the link contacts found by lanes [src0, src0+G); returns the sum of the impulses on the link.
+template <int G>
 DEV V3 apply_link_hits(const LinkHit& s, int src0, bool mine, V3 axis, float& slide, float ims, V3& v, V3& w, float im,
                        float ii, float mu) {
   const unsigned hb = __ballot_sync(kFull, s.hit);
   V3 acc = mk(0, 0, 0);
-  unsigned todo = (hb | (hb >> 8) | (hb >> 16) | (hb >> 24)) & 0xffu;
+  unsigned todo = fold<G>(hb);
   while (todo) {
     const int j = __ffs(todo) - 1;
     todo &= todo - 1;
@@ -242,7 +275,7 @@ DEV V3 apply_link_hits(const LinkHit& s, int src0, bool mine, V3 axis, float& sl
 
 // hand pose + twist; sin/cos of joint j are computed by lane j of the team (one sincosf site) and broadcast
 DEV void team_fk(const PandaParams& P, const float* q, const float* qd, const TeamLane& t, Hand& H) {
-  const int j = min(t.lane & 15, 6);
+  const int j = min(t.tl, 6);
   float qj = q[0];
 #pragma unroll
   for (int i = 1; i < 7; ++i) { if (j == i) qj = q[i]; }
@@ -279,11 +312,13 @@ DEV void team_fk(const PandaParams& P, const float* q, const float* qd, const Te
 
 // The whole rollout of one sample by one team. `k` = row of the sample in this shard's buffers (or -1 for a producer
 // team replaying a row of another shard), `kg` its global id. Producer teams publish refs instead of costs.
+template <int CPL>
 DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBufs& b, const TeamLane& t, int k, int kg,
                       bool valid, bool producer, int which) {
   constexpr int NU = 9;
+  constexpr int G = TeamShape<CPL>::kGroup, TM = TeamShape<CPL>::kTeam;
   const int K = c.K, T = c.T, ns = c.substeps;
-  const bool writer = valid && (t.lane & (kTeam - 1)) == 0;
+  const bool writer = valid && t.tl == 0;
   const bool use_refs = b.refs != nullptr;
   const int g = t.g;
   const float h = c.dt / (float)ns, D = P.drive_damping;
@@ -300,7 +335,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
   float u[NU];
 #pragma unroll
   for (int d = 0; d < NU; ++d) u[d] = 0.0f;
-  // group-partial impulse sums (identical in the 8 lanes of a group), lane-partial penalty sums, per step
+  // group-partial impulse sums (identical in the lanes of a group), lane-partial penalty sums, per step
   V3 imp_table = mk(0, 0, 0), imp_shelf = mk(0, 0, 0), imp_cubeb = mk(0, 0, 0), pen = mk(0, 0, 0);
 
   const int n_iter = T * ns;
@@ -316,7 +351,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       if (c.noise_mode == M3P2I_NOISE_PHILOX && !c.open_loop) {
         // the three Philox blocks (dims 0-3, 4-7, 8) are drawn by lanes 0..2 of the team and broadcast
         float z[4];
-        normal4(c.seed_lo, c.seed_hi, (uint32_t)kg, (uint32_t)step, (uint32_t)min(t.lane & 15, 2), z);
+        normal4(c.seed_lo, c.seed_hi, (uint32_t)kg, (uint32_t)step, (uint32_t)min(t.tl, 2), z);
         float zz[NU];
 #pragma unroll
         for (int d = 0; d < NU; ++d) zz[d] = __shfl_sync(kFull, z[d & 3], t.team_base + (d >> 2));
@@ -327,21 +362,25 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       imp_table = mk(0, 0, 0); imp_shelf = mk(0, 0, 0); imp_cubeb = mk(0, 0, 0); pen = mk(0, 0, 0);
     }
     if (!last) {
-      // ---- 1. joint drives: lane j of the team integrates joint j, the nine results are broadcast
-      const int j = min(t.lane & 15, 8);
-      float qj = e.q[0], vj = e.qd[0], uj = u[0];
+      // ---- 1. joint drives: lane j of the team integrates joint j (an 8-lane team takes a second round for the
+      // ninth joint), the nine results are broadcast
 #pragma unroll
-      for (int i = 1; i < 9; ++i) { if (j == i) { qj = e.q[i]; vj = e.qd[i]; uj = u[i]; } }
-      const float m = j < 7 ? P.arm_inertia : P.finger_mass;
-      float vs = (m * vj + h * D * uj) / (m + h * D);
-      const float f = D * (uj - vs);
-      if (f > P.effort[j]) vs = vj + h * P.effort[j] / m;
-      else if (f < -P.effort[j]) vs = vj - h * P.effort[j] / m;
-      vs = clampf(vs, -P.qd_limit[j], P.qd_limit[j]);
-      if (qj <= P.q_lower[j] && vs < 0.0f) vs = 0.0f;
-      if (qj >= P.q_upper[j] && vs > 0.0f) vs = 0.0f;
+      for (int j0 = 0; j0 < 9; j0 += TM) {
+        const int j = min(j0 + t.tl, 8);
+        float qj = e.q[j0], vj = e.qd[j0], uj = u[j0];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) e.qd[i] = __shfl_sync(kFull, vs, t.team_base + i);
+        for (int i = j0 + 1; i < 9; ++i) { if (j == i) { qj = e.q[i]; vj = e.qd[i]; uj = u[i]; } }
+        const float m = j < 7 ? P.arm_inertia : P.finger_mass;
+        float vs = (m * vj + h * D * uj) / (m + h * D);
+        const float f = D * (uj - vs);
+        if (f > P.effort[j]) vs = vj + h * P.effort[j] / m;
+        else if (f < -P.effort[j]) vs = vj - h * P.effort[j] / m;
+        vs = clampf(vs, -P.qd_limit[j], P.qd_limit[j]);
+        if (qj <= P.q_lower[j] && vs < 0.0f) vs = 0.0f;
+        if (qj >= P.q_upper[j] && vs > 0.0f) vs = 0.0f;
+#pragma unroll
+        for (int i = j0; i < 9 && i < j0 + TM; ++i) e.qd[i] = __shfl_sync(kFull, vs, t.team_base + i - j0);
+      }
     }
     // ---- forward kinematics at the current joint positions (the only FK site)
     Hand H;
@@ -351,7 +390,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       // ---- cost of the step that just ended (same joint positions as this FK; the drives only changed velocities)
       const int ps = step - 1;
       if (producer) {
-        if ((t.lane & 15) == 0 && (which == 0 || c.multi_modal)) ref_publish(b, which, ps, c.epoch, e.cu, !c.multi_modal);
+        if (t.tl == 0 && (which == 0 || (which == 1 && c.multi_modal))) ref_publish(b, which, ps, c.epoch, e.cu, !c.multi_modal);
       } else {
         const int src = t.team_base;  // a lane of group 0 holds cubeA
         Cube a;
@@ -395,11 +434,14 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     // inside the contact loops (26 instructions per use, 12 % of all instructions in a grasp state)
     asm volatile("" : "+f"(cb.R.cx.x), "+f"(cb.R.cx.y), "+f"(cb.R.cx.z), "+f"(cb.R.cy.x), "+f"(cb.R.cy.y), "+f"(cb.R.cy.z),
                       "+f"(cb.R.cz.x), "+f"(cb.R.cz.y), "+f"(cb.R.cz.z));
-    const V3 pc = box_corner(cb, t.c);  // own corner
     V3 v = e.cu.v, w = e.cu.w;
     const V3 x = e.cu.p;
+    // own corners, as lever arms about the cube centre (corner = x + ra); slot s is corner t.c + s * G
+    V3 ra[CPL];
+#pragma unroll
+    for (int sl = 0; sl < CPL; ++sl) ra[sl] = corner_arm(cb, t.c + sl * G);
     // the other cube of the sample (for cube-cube contact)
-    const V3 xo = shfl3(x, t.lane ^ 8);
+    const V3 xo = shfl3(x, t.other);
     bool cc_near;
     {
       const V3 d = xo - x;
@@ -409,16 +451,21 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     OBox3 ob;
     ob.c = xo; ob.half = half_oth; ob.R = cb.R;
     if (__any_sync(kFull, cc_near)) {
-      ob.R.cx = shfl3(cb.R.cx, t.lane ^ 8); ob.R.cy = shfl3(cb.R.cy, t.lane ^ 8); ob.R.cz = shfl3(cb.R.cz, t.lane ^ 8);
+      ob.R.cx = shfl3(cb.R.cx, t.other); ob.R.cy = shfl3(cb.R.cy, t.other); ob.R.cz = shfl3(cb.R.cz, t.other);
       // exact test of the thread-per-sample code: sphere of cubeA against the box of cubeB
       cc_near = cc_near && (g == 0 ? boxes_near(cb, ob, P.contact_margin) : boxes_near(ob, cb, P.contact_margin));
     }
-    // which fixed boxes / link boxes are close to the own cube, decided once per sub-step
-    // lane c of a group tests fixed box c (n_static <= 8); the group's verdicts are collected with one ballot
-    const bool near_c = t.c < P.n_static && boxes_near(cb, obox_of(P.st[min(t.c, P.n_static - 1)]), P.contact_margin);
-    const unsigned near_bal = __ballot_sync(kFull, near_c);
-    const unsigned near_mask = (near_bal >> t.group_base) & 0xffu;
-    const unsigned near_any = (near_bal | (near_bal >> 8) | (near_bal >> 16) | (near_bal >> 24)) & 0xffu;
+    // which fixed boxes / link boxes are close to the own cube, decided once per sub-step:
+    // lane c of a group tests fixed boxes c, c + G, ... (n_static <= 8); one ballot per slot collects the verdicts
+    unsigned near_mask = 0u, near_any = 0u;
+#pragma unroll
+    for (int sl = 0; sl < CPL; ++sl) {
+      const int kb = t.c + sl * G;
+      const bool near_c = kb < P.n_static && boxes_near(cb, obox_of(P.st[min(kb, P.n_static - 1)]), P.contact_margin);
+      const unsigned bal = __ballot_sync(kFull, near_c);
+      near_mask |= ((bal >> t.group_base) & ((1u << G) - 1u)) << (sl * G);
+      near_any |= fold<G>(bal) << (sl * G);
+    }
     unsigned lnear = 0u;
 #pragma unroll 1
     for (int f = 0; f < 3; ++f) {
@@ -430,12 +477,17 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       if (dot(dl, dl) > rr * rr) continue;
       if (boxes_near(lb, cb, P.contact_margin)) lnear |= 1u << f;
     }
-
-    // geometry-only part of the own corner's fixed-box contacts (see StaticHit)
-    const V3 ra = pc - x;
+    // geometry-only part of the own corners' contacts with the first near fixed box (see StaticHit); it is almost
+    // always the only one (the table), so the passes below reuse it
     const float inv_h = __frcp_rn(h);
     const int ks0 = near_any ? __ffs(near_any) - 1 : 0;
-    const StaticHit sh0 = static_hit(near_any && ((near_mask >> ks0) & 1u), pc, ra, obox_of(P.st[ks0]), im, ii, inv_h, P);
+    StaticHit sh0[CPL];
+    {
+      const OBox3 sb = obox_of(P.st[ks0]);
+      const bool near0 = near_any && ((near_mask >> ks0) & 1u);
+#pragma unroll
+      for (int sl = 0; sl < CPL; ++sl) sh0[sl] = static_hit(near0, x + ra[sl], ra[sl], sb, im, ii, inv_h, P);
+    }
 
 #pragma unroll 1
     for (int p = 0; p < c.passes; ++p) {
@@ -445,10 +497,16 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
         const int ks = __ffs(todo_k) - 1;
         const OBox3 sb = obox_of(P.st[ks]);
         const bool near = (near_mask >> ks) & 1u;
-        // the first near box (almost always the only one: the table) was tested before the pass loop
-        const StaticHit sh = ks == ks0 ? sh0 : static_hit(near, pc, ra, sb, im, ii, inv_h, P);
         const float mu = 0.5f * (mu_c + P.st[ks].mu);
-        const V3 got = apply_static_hits(sh, ra, t.group_base, v, w, im, ii, mu);
+        V3 got = mk(0, 0, 0);
+#pragma unroll 1
+        for (int sl = 0; sl < CPL; ++sl) {
+          const V3 r = (CPL > 1 && sl > 0) ? ra[CPL - 1] : ra[0];
+          StaticHit sh;
+          if (ks == ks0) sh = (CPL > 1 && sl > 0) ? sh0[CPL - 1] : sh0[0];
+          else sh = static_hit(near, x + r, r, sb, im, ii, inv_h, P);
+          got = got + apply_static_hits<G>(sh, r, t.group_base, v, w, im, ii, mu);
+        }
         // impulses received by the fixed box = -(impulses on the cube)
         if (ks == P.idx_table) imp_table = imp_table - got;
         if (ks == P.idx_shelf) imp_shelf = imp_shelf - got;
@@ -456,20 +514,22 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       }
       // (b) cubeA against cubeB, both ways; every lane of the team applies every impulse to replicas of both cubes
       if (__any_sync(kFull, cc_near)) {
-        const V3 vo = shfl3(v, t.lane ^ 8), wo = shfl3(w, t.lane ^ 8);
+        const V3 vo = shfl3(v, t.other), wo = shfl3(w, t.other);
         Dyn3 A = g == 0 ? dyn_cube(v, w, x, im, ii) : dyn_cube(vo, wo, xo, imo, iio);   // cubeA
         Dyn3 B = g == 0 ? dyn_cube(vo, wo, xo, imo, iio) : dyn_cube(v, w, x, im, ii);   // cubeB
         const float mu = 0.5f * (P.cube_mu[0] + P.cube_mu[1]);
         V3 got = mk(0, 0, 0);
 #pragma unroll 1
-        for (int ph = 0; ph < 2; ++ph) {
+        for (int phs = 0; phs < 2 * CPL; ++phs) {
           // ph 0: corners of cubeA in cubeB (found by group 0), normal out of cubeB;
           // ph 1: corners of cubeB in cubeA (found by group 1), normal out of cubeA -> solve with -n
+          const int ph = phs / CPL, sl = phs - ph * CPL;
+          const V3 pc = x + ((CPL > 1 && sl > 0) ? ra[CPL - 1] : ra[0]);
           V3 n = mk(0, 0, 0);
           float depth = 0.0f;
           const bool hit = cc_near && g == ph && point_in_box(pc, ob, P.contact_margin, n, depth);
           const float sg = ph == 0 ? 1.0f : -1.0f;
-          got = got + apply_hits(hit, n, depth, pc, t.team_base + 8 * ph, cc_near, [&](V3 nj, float dj, V3 pj) {
+          got = got + apply_hits<G>(hit, n, depth, pc, t.team_base + G * ph, cc_near, [&](V3 nj, float dj, V3 pj) {
             return solve_contact3_call(A, B, sg * nj, dj, pj, mu, h, P);
           });
         }
@@ -492,13 +552,13 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
           const float ims = f < 2 ? 1.0f / P.finger_mass : 0.0f;
           float sl_f = f == 0 ? slide[0] : (f == 1 ? slide[1] : 0.0f);
           const float mu = 0.5f * (P.robot_mu + mu_c);
-          const V3 lp = box_corner(lb, t.c);
           V3 got = mk(0, 0, 0);
 #pragma unroll 1
-          for (int ph = 0; ph < 2; ++ph) {
+          for (int phs = 0; phs < 2 * CPL; ++phs) {
             // ph 0: corners of the link box in the cube, normal out of the cube;
             // ph 1: corners of the cube in the link box, normal out of the link -> solve with -n
-            const V3 pt = ph == 0 ? lp : pc;
+            const int ph = phs / CPL, sl = phs - ph * CPL;
+            const V3 pt = ph == 0 ? box_corner(lb, t.c + sl * G) : x + ((CPL > 1 && sl > 0) ? ra[CPL - 1] : ra[0]);
             OBox3 bx;
             bx.c = sel3(ph == 0, cb.c, lb.c); bx.half = sel3(ph == 0, cb.half, lb.half);
             bx.R.cx = sel3(ph == 0, cb.R.cx, lb.R.cx); bx.R.cy = sel3(ph == 0, cb.R.cy, lb.R.cy);
@@ -507,13 +567,13 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
             float depth = 0.0f;
             const bool hit = mine && point_in_box(pt, bx, P.contact_margin, n, depth);
             const float sg = ph == 0 ? 1.0f : -1.0f;
-            const LinkHit lh = link_hit(hit, sg * n, depth, pt, H, axis, ims, x, im, ii, inv_h, P);
-            got = got + apply_link_hits(lh, t.team_base + 8 * i, mine, axis, sl_f, ims, v, w, im, ii, mu);
+            const LinkHit lh = link_hit(hit, sg * n, depth, pt, H.v, H.w, H.p, axis, ims, x, im, ii, inv_h, P);
+            got = got + apply_link_hits<G>(lh, t.team_base + G * i, mine, axis, sl_f, ims, v, w, im, ii, mu);
           }
           if (mine && i == 1) imp_cubeb = imp_cubeb - got;
           // the finger's sliding speed is shared by both groups: take it from the group that worked the pair
-          const float sl = __shfl_sync(kFull, sl_f, t.team_base + 8 * i);
-          const bool worked = __shfl_sync(kFull, (int)mine, t.team_base + 8 * i) != 0;
+          const float sl = __shfl_sync(kFull, sl_f, t.team_base + G * i);
+          const bool worked = __shfl_sync(kFull, (int)mine, t.team_base + G * i) != 0;
           if (worked && f == 0) slide[0] = sl;
           if (worked && f == 1) slide[1] = sl;
         }
@@ -540,19 +600,22 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
           OBox3 lb;
           lb.c = f == 0 ? lc[0] : (f == 1 ? lc[1] : lc[2]); lb.R = H.R; lb.half = f < 2 ? fhalf : hhalf;
           if (!boxes_near(lb, sb, 0.0f)) continue;
-          const V3 lp = box_corner(lb, t.c);
-          V3 n; float depth;
-          if (!point_in_box(lp, sb, 0.0f, n, depth)) continue;
-          const float fn = P.penalty_stiffness * depth;
-          V3 vel = H.v + cross(H.w, lp - H.p);
-          if (f == 0) vel = vel + slide[0] * H.R.cy;
-          if (f == 1) vel = vel - slide[1] * H.R.cy;
-          const float vn = dot(vel, n);
-          const V3 tv = vel - vn * n;
-          const float vt = sqrtf(dot(tv, tv));
-          V3 fo = (-fn) * n;
-          if (vt > 1e-6f) fo = fo + (mu * fn / vt) * tv;
-          pen = pen + fo;
+#pragma unroll 1
+          for (int sl = 0; sl < CPL; ++sl) {
+            const V3 lp = box_corner(lb, t.c + sl * G);
+            V3 n; float depth;
+            if (!point_in_box(lp, sb, 0.0f, n, depth)) continue;
+            const float fn = P.penalty_stiffness * depth;
+            V3 vel = H.v + cross(H.w, lp - H.p);
+            if (f == 0) vel = vel + slide[0] * H.R.cy;
+            if (f == 1) vel = vel - slide[1] * H.R.cy;
+            const float vn = dot(vel, n);
+            const V3 tv = vel - vn * n;
+            const float vt = sqrtf(dot(tv, tv));
+            V3 fo = (-fn) * n;
+            if (vt > 1e-6f) fo = fo + (mu * fn / vt) * tv;
+            pen = pen + fo;
+          }
         }
       }
     }
@@ -579,10 +642,10 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       // ---- end of the step: reported contact forces, per-step stores
       V3 pr = pen;
 #pragma unroll
-      for (int o = 1; o < 8; o <<= 1) pr = pr + shfl3(pr, t.lane ^ o);
-      const V3 pen_o = shfl3(pr, t.lane ^ 8);
+      for (int o = 1; o < G; o <<= 1) pr = pr + shfl3(pr, t.lane ^ o);
+      const V3 pen_o = shfl3(pr, t.other);
       const V3 pen_table = g == 0 ? pr : pen_o, pen_shelf = g == 0 ? pen_o : pr;
-      const V3 it_o = shfl3(imp_table, t.lane ^ 8), is_o = shfl3(imp_shelf, t.lane ^ 8), ib_o = shfl3(imp_cubeb, t.lane ^ 8);
+      const V3 it_o = shfl3(imp_table, t.other), is_o = shfl3(imp_shelf, t.other), ib_o = shfl3(imp_cubeb, t.other);
       const V3 itab = g == 0 ? imp_table + it_o : it_o + imp_table;   // cubeA's share first, as in the serial order
       const V3 ishf = g == 0 ? imp_shelf + is_o : is_o + imp_shelf;
       const V3 icb = g == 1 ? imp_cubeb : ib_o;

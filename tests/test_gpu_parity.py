@@ -222,7 +222,7 @@ GRASP_Q = [-0.21448, 1.040633, -0.091726, -1.527796, 0.144743, 2.56178, 0.807333
 
 @pytest.mark.parametrize("task,mm,shelf", [("pick", False, False), ("reach", True, True), ("reach", False, False)])
 def test_team_and_thread_kernels_agree(task, mm, shelf):
-    """The lane-cooperative (16 lanes per sample) and the thread-per-sample rollout kernels apply the same impulses
+    """The lane-cooperative (8 and 16 lanes per sample) and the thread-per-sample rollout kernels apply the same impulses
     in the same order (only the summation order of the reported contact forces differs), and both follow the oracle.
     `pick` starts with the fingers closed around cubeA (finger / cube / table contacts in every rollout). Stick /
     slip contact dynamics amplify fp32 rounding differences (FMA contraction, SFU division) step by step: measured on
@@ -232,7 +232,7 @@ def test_team_and_thread_kernels_agree(task, mm, shelf):
     case = ("x", "panda_env", task, None, 512, 16, mm, shelf, None)
     budget = 0.10 if task == "pick" else 0.005
     res = {}
-    for lanes in (1, 16):
+    for lanes in (1, 8, 16):
         cfg, o, n = _setup(case, A.NOISE_PHILOX)
         n.close()
         cfg.mppi.lanes_per_sample = lanes
@@ -262,12 +262,13 @@ def test_team_and_thread_kernels_agree(task, mm, shelf):
         res[lanes] = outs
         o.close()
         n.close()
-    for i in range(3):
-        assert_close(res[16][i][0], res[1][i][0], 2e-2, 2e-2, f"team vs thread action [{i}]")
-        for j, what in ((1, "states"), (2, "cost_horizon")):
-            frac = _sample_mismatch(res[16][i][j], res[1][i][j], RTOL, ATOL)
-            assert frac <= budget, f"team vs thread {what} [{i}]: {frac:.3f} of the samples differ"
-            assert np.median(np.abs(res[16][i][j] - res[1][i][j])) < 5e-4
+    for team in (8, 16):
+        for i in range(3):
+            assert_close(res[team][i][0], res[1][i][0], 2e-2, 2e-2, f"team{team} vs thread action [{i}]")
+            for j, what in ((1, "states"), (2, "cost_horizon")):
+                frac = _sample_mismatch(res[team][i][j], res[1][i][j], RTOL, ATOL)
+                assert frac <= budget, f"team{team} vs thread {what} [{i}]: {frac:.3f} of the samples differ"
+                assert np.median(np.abs(res[team][i][j] - res[1][i][j])) < 5e-4
 
 
 @pytest.mark.parametrize("env,task,K,T", [("panda_env", "pick", 21, 9), ("panda_env", "reach", 20, 64), ("point_env", "push", 33, 64),
