@@ -184,7 +184,9 @@ typedef struct M3P2IPandaScene {
   int32_t n_actors;
   int32_t idx_table;     /* index into statics[] of the bodies named by get_motion_cost (cost_functions.py:161-164) */
   int32_t idx_shelf;
-  int32_t reserved[2];
+  int32_t link_sweeps;   /* Gauss-Seidel sweeps over the finger/hand-cube contacts inside each solver pass (<= 0: 4):
+                            the finger - cube - finger chain of a grasp needs them to settle within a sub-step */
+  int32_t reserved;
   M3P2IBody cube_a;      /* 5_cubeA.yaml */
   M3P2IBody cube_b;      /* 6_cubeB.yaml */
   M3P2IBox statics[M3P2I_MAX_STATIC];

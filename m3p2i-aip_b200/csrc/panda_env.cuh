@@ -476,6 +476,8 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
           if (i == 1) imp_cubeb = imp_cubeb - accS;
         }
       box_vs_box3<true>(C[0], cbox[0], C[1], cbox[1], 0.5f * (P.cube_mu[0] + P.cube_mu[1]), h, P, imp_cubeb);
+      // the finger - cube - finger chain of a grasp settles only after a few sweeps over its own contacts
+      for (int sw = 0; sw < P.link_sweeps; ++sw)
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
         V3 sink = mk(0, 0, 0);

@@ -231,11 +231,11 @@ DEV LinkHit link_hit(bool hit, V3 n, float depth, V3 pt, V3 hv, V3 hw, V3 hp, V3
   return s;
 }
 
-// Serial application of the link contacts found by lanes [src0, src0+G); returns the sum of the impulses on the link.
+// Serial application of the link contacts found by lanes [src0, src0+G) (hb = warp ballot of s.hit); returns the sum
+// of the impulses on the link.
 template <int G>
-DEV V3 apply_link_hits(const LinkHit& s, int src0, bool mine, V3 axis, float& slide, float ims, V3& v, V3& w, float im,
-                       float ii, float mu) {
-  const unsigned hb = __ballot_sync(kFull, s.hit);
+DEV V3 apply_link_hits(const LinkHit& s, unsigned hb, int src0, bool mine, V3 axis, float& slide, float ims, V3& v, V3& w,
+                       float im, float ii, float mu) {
   V3 acc = mk(0, 0, 0);
   unsigned todo = fold<G>(hb);
   while (todo) {
@@ -481,6 +481,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     // always the only one (the table), so the passes below reuse it
     const float inv_h = __frcp_rn(h);
     const int ks0 = near_any ? __ffs(near_any) - 1 : 0;
+    unsigned live = 0xffffffu;  // link contact slots (pair fi, direction/slot phs) not yet known to be empty
     StaticHit sh0[CPL];
     {
       const OBox3 sb = obox_of(P.st[ks0]);
@@ -539,43 +540,52 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
           if (g == 1) imp_cubeb = imp_cubeb - got;  // cubeB received -(impulse on cubeA)
         }
       }
-      // (c) links against the cubes in the order (f, cubeA), (f, cubeB); pair (f, i) is worked by group i
+      // (c) links against the cubes in the order (f, cubeA), (f, cubeB); pair (f, i) is worked by group i.
+      // P.link_sweeps sweeps: the finger - cube - finger chain of a grasp only settles after a few sweeps over its
+      // own contacts. `live` remembers which (pair, direction, slot) found no contact at all in this sub-step
+      // (positions are fixed), so later sweeps and passes skip their detection.
       if (__any_sync(kFull, lnear != 0u)) {
 #pragma unroll 1
-        for (int fi = 0; fi < 6; ++fi) {
-          const int f = fi >> 1, i = fi & 1;
-          const bool mine = g == i && ((lnear >> f) & 1u);
-          if (!__any_sync(kFull, mine)) continue;
-          OBox3 lb;
-          lb.c = f == 0 ? lc[0] : (f == 1 ? lc[1] : lc[2]); lb.R = H.R; lb.half = f < 2 ? fhalf : hhalf;
-          const V3 axis = f == 0 ? H.R.cy : (f == 1 ? -H.R.cy : mk(0, 0, 0));
-          const float ims = f < 2 ? 1.0f / P.finger_mass : 0.0f;
-          float sl_f = f == 0 ? slide[0] : (f == 1 ? slide[1] : 0.0f);
-          const float mu = 0.5f * (P.robot_mu + mu_c);
-          V3 got = mk(0, 0, 0);
+        for (int sw = 0; sw < P.link_sweeps; ++sw) {
 #pragma unroll 1
-          for (int phs = 0; phs < 2 * CPL; ++phs) {
-            // ph 0: corners of the link box in the cube, normal out of the cube;
-            // ph 1: corners of the cube in the link box, normal out of the link -> solve with -n
-            const int ph = phs / CPL, sl = phs - ph * CPL;
-            const V3 pt = ph == 0 ? box_corner(lb, t.c + sl * G) : x + ((CPL > 1 && sl > 0) ? ra[CPL - 1] : ra[0]);
-            OBox3 bx;
-            bx.c = sel3(ph == 0, cb.c, lb.c); bx.half = sel3(ph == 0, cb.half, lb.half);
-            bx.R.cx = sel3(ph == 0, cb.R.cx, lb.R.cx); bx.R.cy = sel3(ph == 0, cb.R.cy, lb.R.cy);
-            bx.R.cz = sel3(ph == 0, cb.R.cz, lb.R.cz);
-            V3 n = mk(0, 0, 0);
-            float depth = 0.0f;
-            const bool hit = mine && point_in_box(pt, bx, P.contact_margin, n, depth);
-            const float sg = ph == 0 ? 1.0f : -1.0f;
-            const LinkHit lh = link_hit(hit, sg * n, depth, pt, H.v, H.w, H.p, axis, ims, x, im, ii, inv_h, P);
-            got = got + apply_link_hits<G>(lh, t.team_base + G * i, mine, axis, sl_f, ims, v, w, im, ii, mu);
+          for (int fi = 0; fi < 6; ++fi) {
+            const int f = fi >> 1, i = fi & 1;
+            const bool mine = g == i && ((lnear >> f) & 1u);
+            if (!((live >> (4 * fi)) & 0xfu) || !__any_sync(kFull, mine)) continue;
+            OBox3 lb;
+            lb.c = f == 0 ? lc[0] : (f == 1 ? lc[1] : lc[2]); lb.R = H.R; lb.half = f < 2 ? fhalf : hhalf;
+            const V3 axis = f == 0 ? H.R.cy : (f == 1 ? -H.R.cy : mk(0, 0, 0));
+            const float ims = f < 2 ? 1.0f / P.finger_mass : 0.0f;
+            float sl_f = f == 0 ? slide[0] : (f == 1 ? slide[1] : 0.0f);
+            const float mu = 0.5f * (P.robot_mu + mu_c);
+            V3 got = mk(0, 0, 0);
+#pragma unroll 1
+            for (int phs = 0; phs < 2 * CPL; ++phs) {
+              // ph 0: corners of the link box in the cube, normal out of the cube;
+              // ph 1: corners of the cube in the link box, normal out of the link -> solve with -n
+              if (!((live >> (4 * fi + phs)) & 1u)) continue;
+              const int ph = phs / CPL, sl = phs - ph * CPL;
+              const V3 pt = ph == 0 ? box_corner(lb, t.c + sl * G) : x + ((CPL > 1 && sl > 0) ? ra[CPL - 1] : ra[0]);
+              OBox3 bx;
+              bx.c = sel3(ph == 0, cb.c, lb.c); bx.half = sel3(ph == 0, cb.half, lb.half);
+              bx.R.cx = sel3(ph == 0, cb.R.cx, lb.R.cx); bx.R.cy = sel3(ph == 0, cb.R.cy, lb.R.cy);
+              bx.R.cz = sel3(ph == 0, cb.R.cz, lb.R.cz);
+              V3 n = mk(0, 0, 0);
+              float depth = 0.0f;
+              const bool hit = mine && point_in_box(pt, bx, P.contact_margin, n, depth);
+              const unsigned hb = __ballot_sync(kFull, hit);
+              if (!hb) { live &= ~(1u << (4 * fi + phs)); continue; }
+              const float sg = ph == 0 ? 1.0f : -1.0f;
+              const LinkHit lh = link_hit(hit, sg * n, depth, pt, H.v, H.w, H.p, axis, ims, x, im, ii, inv_h, P);
+              got = got + apply_link_hits<G>(lh, hb, t.team_base + G * i, mine, axis, sl_f, ims, v, w, im, ii, mu);
+            }
+            if (mine && i == 1) imp_cubeb = imp_cubeb - got;
+            // the finger's sliding speed is shared by both groups: take it from the group that worked the pair
+            const float sl = __shfl_sync(kFull, sl_f, t.team_base + G * i);
+            const bool worked = __shfl_sync(kFull, (int)mine, t.team_base + G * i) != 0;
+            if (worked && f == 0) slide[0] = sl;
+            if (worked && f == 1) slide[1] = sl;
           }
-          if (mine && i == 1) imp_cubeb = imp_cubeb - got;
-          // the finger's sliding speed is shared by both groups: take it from the group that worked the pair
-          const float sl = __shfl_sync(kFull, sl_f, t.team_base + G * i);
-          const bool worked = __shfl_sync(kFull, (int)mine, t.team_base + G * i) != 0;
-          if (worked && f == 0) slide[0] = sl;
-          if (worked && f == 1) slide[1] = sl;
         }
       }
     }

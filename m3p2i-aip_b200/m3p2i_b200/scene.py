@@ -222,6 +222,7 @@ def build_panda_scene(actors=None):
     s.slop = 0.0005
     s.max_corr_vel = 0.5
     s.penalty_stiffness = 2000.0
+    s.link_sweeps = 4
     s.n_actors = len(actors)
     s.idx_table = -1
     s.idx_shelf = -1

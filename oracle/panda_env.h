@@ -412,9 +412,11 @@ static inline void o_panda_step(OPandaEnv* e, const M3P2IPandaScene* sc, const M
           o_box_vs_box3(&C[i], &cbox[i], &S, &sb, 0.5f * (bp[i]->mu + sc->statics[k].mu), h, sc, 0);
         }
       o_box_vs_box3(&C[0], &cbox[0], &C[1], &cbox[1], 0.5f * (bp[0]->mu + bp[1]->mu), h, sc, 1);
-      for (int f = 0; f < 3; ++f)
-        for (int i = 0; i < 2; ++i)
-          o_box_vs_box3(&L[f], &lbox[f], &C[i], &cbox[i], 0.5f * (sc->robot_mu + bp[i]->mu), h, sc, 1);
+      /* the finger - cube - finger chain of a grasp settles only after a few sweeps over its own contacts */
+      for (int sw = 0; sw < (sc->link_sweeps > 0 ? sc->link_sweeps : 4); ++sw)
+        for (int f = 0; f < 3; ++f)
+          for (int i = 0; i < 2; ++i)
+            o_box_vs_box3(&L[f], &lbox[f], &C[i], &cbox[i], 0.5f * (sc->robot_mu + bp[i]->mu), h, sc, 1);
     }
     /* finger speed limit also holds after contacts */
     for (int j = 7; j < 9; ++j) e->qd[j] = q_clamp(e->qd[j], -sc->qd_limit[j], sc->qd_limit[j]);

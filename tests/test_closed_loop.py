@@ -137,3 +137,54 @@ def test_panda_reach_gpu():
         if best < cfg.pre_height_diff + 0.005:
             break
     assert best < cfg.pre_height_diff + 0.02, f"closest approach {best:.3f} m after {i + 1} ticks"
+
+
+GRASP_Q = [-0.21448, 1.040633, -0.091726, -1.527796, 0.144743, 2.56178, 0.807333, 0.04, 0.04]  # open fingers astride cubeA
+
+
+def _squeeze_and_lift(factory):
+    """Fingers close on cubeA resting on the table (gripper command "close", mppi.py:415-416), hold, then the arm
+    lifts. Returns per-tick finger openings, table contact forces and cube positions."""
+    cfg = S.make_cfg("panda_env", "pick", None, 1, 16)
+    real = wrapper.IsaacGymWrapper(cfg.isaacgym, "panda_env", num_envs=1, device="cpu", backend_factory=factory)
+    for _ in range(30):
+        real.step()   # the cubes settle on the table
+    real._dof_state[0, 0::2] = torch.tensor(GRASP_Q)
+    real._dof_state[0, 1::2] = 0
+    real.set_dof_state_tensor(real._dof_state)
+    fingers, f_table, cube = [], [], []
+    for i in range(70):
+        a = torch.zeros(1, 9)
+        a[0, 7:] = -1.5
+        if i >= 40:
+            a[0, 1], a[0, 3] = -0.5, 0.5   # shoulder back, elbow up: the hand rises
+        real.set_dof_velocity_target_tensor(a)
+        real.step()
+        fingers.append(real._dof_state[0, [14, 16]].clone().numpy())
+        f_table.append(real.get_actor_contact_forces_by_name("table", "box")[0].clone().numpy())
+        cube.append(real.get_actor_link_by_name("cubeA", "box")[0, :3].clone().numpy())
+    return np.array(fingers), np.array(f_table), np.array(cube)
+
+
+def _check_grasp(fingers, f_table, cube):
+    hold = slice(10, 40)
+    # the fingers stop on the cube faces and stay there (no sinking into the cube under the 20 N drive)
+    assert fingers[hold].min() > 0.030, fingers[hold].min()
+    assert np.abs(fingers[39] - fingers[10]).max() < 1e-3
+    # a settled squeeze puts no tangential load on the table: below the 0.1 N threshold of get_motion_cost
+    # (cost_functions.py:165-169), and the cube does not creep
+    assert np.abs(f_table[hold, :2]).sum(axis=1).max() < 0.1, np.abs(f_table[hold, :2]).sum(axis=1).max()
+    assert np.linalg.norm(cube[39] - cube[10]) < 1e-3
+    # lifted with the gripper: off the table (only cubeB's weight is left on it), still between the fingers
+    assert cube[-1, 2] - cube[39, 2] > 0.05, cube[-1] - cube[39]
+    assert abs(f_table[-1, 2] + 0.125 * 9.8) < 0.05, f_table[-1]
+    assert fingers[-1].min() > 0.024
+
+
+def test_grasp_holds_and_lifts_cpu():
+    _check_grasp(*_squeeze_and_lift(O.Oracle.for_sim))
+
+
+@pytest.mark.gpu
+def test_grasp_holds_and_lifts_gpu():
+    _check_grasp(*_squeeze_and_lift(None))
