@@ -291,6 +291,7 @@ RolloutCfg make_rcfg(const H* h) {
   r.substeps = c.substeps; r.passes = c.solver_passes; r.task = h->task; r.gripper = h->gripper;
   r.env_live = h->env_live ? 1 : 0; r.store_env = h->env_alloc ? 1 : 0; r.open_loop = 0;
   r.lanes = rollout_lanes(h);
+  { static int a = -1; if (a < 0) { const char* e = getenv("M3P2I_TEAM_ALIGN"); a = e ? atoi(e) : 1; } r.align = a; }
   r.dt = c.dt; r.gamma = c.gamma; r.u_scale = c.u_scale; r.kp_suction = c.kp_suction;
   r.pre_height_diff = c.pre_height_diff; r.tilt_cos = c.tilt_cos_theta;
   memcpy(r.u_min, c.u_min, sizeof(r.u_min)); memcpy(r.u_max, c.u_max, sizeof(r.u_max));

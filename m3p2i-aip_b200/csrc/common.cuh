@@ -58,6 +58,7 @@ struct RolloutCfg {
   int preshifted;   // the stored sequences were already shifted (m3p2i_sample_actions): read them at t, not t+1
   int open_loop;    // actions are supplied (m3p2i_rollout_actions) instead of sampled
   unsigned epoch;   // ref_flags reach epoch + t + 1 when step t of this launch has been published
+  int align;        // team kernel: 1 = re-align the CTA's warps with a barrier every sub-step (I-cache sharing)
   int lanes;        // lanes per sample: 1 = one thread per sample, 16 = lane-cooperative team (panda_env)
   float dt, gamma, u_scale, kp_suction, pre_height_diff, tilt_cos;
   float u_min[kMaxNu], u_max[kMaxNu], sigma[kMaxNu];

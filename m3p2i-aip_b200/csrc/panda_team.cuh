@@ -345,7 +345,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     const bool last = it == n_iter;
     // Re-align the warps of the CTA once per sub-step: they then walk the same stretch of this (large) loop body at
     // about the same time and share its instruction-cache lines instead of evicting each other's.
-    __syncthreads();
+    if (c.align) __syncthreads();
     if (s == 0 && !last) {
       // ---- perturbed action of this step (mppi.py:392-416)
       if (c.noise_mode == M3P2I_NOISE_PHILOX && !c.open_loop) {
