@@ -101,3 +101,57 @@ def test_host_skill_utils_match_reference():
     assert torch.allclose(ours.get_general_ori_cube2goal(a, b), ref.get_general_ori_cube2goal(a, b), atol=1e-5)
     for tilt in (0, 0.5):
         assert torch.allclose(ours.get_general_ori_ee2cube(a, b, tilt), ref.get_general_ori_ee2cube(a, b, tilt), atol=1e-5)
+
+
+class _EpisodeOver(Exception):
+    pass
+
+
+def test_sim_and_reactive_tamp_loop_unchanged(reactive_tamp, monkeypatch, capsys):
+    """The reference's two-process loop, both scripts UNCHANGED: scripts/sim.py (the "real world", sim.py:19-58) drives
+    scripts/reactive_tamp.py's REACTIVE_TAMP through the reference's RPC method names (run_tamp / get_suction; byte
+    frames of data_transfer.py) -- the zerorpc socket is replaced by an in-process client, everything else is the
+    reference's own control flow: update_dyn_obs, play_with_cube, set_dof_velocity_target_tensor,
+    check_and_apply_suction, step, time_tracking. The K=1 env behind sim.py is this repo's integrator."""
+    from m3p2i_b200 import scene as S
+    cfg = S.make_cfg("point_env", "navigation", [1.0, -0.8], 64, 12)
+    cfg.mppi.sampling_method = "halton"
+    tamp = reactive_tamp.REACTIVE_TAMP(cfg)
+    ticks = {"n": 0}
+
+    class Client:
+        def connect(self, addr):
+            assert addr.startswith("tcp://")
+
+        def run_tamp(self, dof_bytes, root_bytes):
+            if ticks["n"] >= 60:
+                raise _EpisodeOver
+            ticks["n"] += 1
+            return tamp.run_tamp(dof_bytes, root_bytes)
+
+        def get_suction(self):
+            return tamp.get_suction()
+
+        def get_trajs(self):
+            return tamp.get_trajs()
+
+    sys.modules["zerorpc"].Client = Client
+    spec = importlib.util.spec_from_file_location("ref_sim", os.path.join(REF, "scripts", "sim.py"))
+    sim_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim_mod)
+    assert sim_mod.wrapper.__file__.startswith(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    monkeypatch.setattr(sim_mod, "time_tracking", lambda t, cfg: t)    # no real-time pacing in a test
+    created = []
+    real_cls = sim_mod.wrapper.IsaacGymWrapper
+
+    def make(*a, **k):
+        import oracle_py as O
+        created.append(real_cls(*a, backend_factory=O.Oracle.for_sim, **k))
+        return created[-1]
+    monkeypatch.setattr(sim_mod.wrapper, "IsaacGymWrapper", make)
+    with pytest.raises(_EpisodeOver):
+        sim_mod.run_sim(cfg)
+    assert ticks["n"] == 60
+    robot = created[0].robot_pos[0]
+    d0 = float(np.linalg.norm(np.array([1.0, -0.8])))
+    assert float(torch.linalg.norm(robot - torch.tensor([1.0, -0.8]))) < 0.5 * d0, robot.tolist()

@@ -36,7 +36,7 @@ class Tamp:
 
 
 cfg = S.make_cfg("panda_env", "reach", None, K, H)
-cfg.mppi.sampling_method = "philox" if factory is None else "halton"
+cfg.mppi.sampling_method = os.environ.get("PICK_SAMPLING", "philox" if factory is None else "halton")
 tamp = Tamp(cfg)
 real = wrapper.IsaacGymWrapper(cfg.isaacgym, "panda_env", num_envs=1, device="cpu", backend_factory=factory)
 for _ in range(30):
