@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: exchange fused into the kernels over NVLink peer memory (default) or two NCCL collectives")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -225,11 +227,21 @@ def main():
     c = S.build_config(cfg, num_samples_local=K_PER_GPU, sample_offset=rank * K_PER_GPU, noise_mode=A.NOISE_PHILOX, seed=0)
     planner = native.NativePlanner(c, S.build_panda_scene(), device=local_rank)
     planner.set_filter_matrix(S.savgol_matrix(HORIZON))
+    exchange = "none"
     if world > 1:
+        exchange = args.exchange
         with stdout_to_stderr():
-            uid = [native.comm_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(uid, src=0)
-            planner.comm_init(rank, world, uid[0])
+            if exchange == "peer":
+                from m3p2i_b200 import sharded
+                try:
+                    sharded.attach_peers(planner)   # raises on every rank if any rank could not map its peers
+                except RuntimeError as exc:
+                    print(f"[rank {rank}] {exc}; using NCCL", file=sys.stderr)
+                    exchange = "nccl (peer memory unavailable)"
+            if exchange != "peer":
+                uid = [native.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(uid, src=0)
+                planner.comm_init(rank, world, uid[0])
     dof, root, goal = scene_inputs()
     planner.set_objective("pick", goal, "close")
     planner.set_state(dof, root)
@@ -303,7 +315,9 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "K_global": Kg, "H": HORIZON, "noise": "philox4x32-10 in-kernel",
-                       "dt": 0.01, "substeps": 2, "solver_passes": 2,
+                       "dt": 0.01, "substeps": 2, "solver_passes": 2, "link_sweeps": 4,
+                       "exchange": {"none": "single rank", "peer": "stores into peer HBM over NVLink from inside the rollout / "
+                                    "weighted-sum kernels (no collective call)"}.get(exchange, exchange),
                        "l2": "not flushed" if flush is None else "flushed between steps (256 MiB fill outside the timed events)",
                        "timing": "CUDA events per step on the launching stream, max over ranks, mean over steps"},
             "e2e": {"value": Kg * HORIZON / e2e_s, "unit": "sample-steps/s", "h2d_bytes_per_step": h2d,

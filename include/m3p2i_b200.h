@@ -325,6 +325,24 @@ int m3p2i_phase_finish(m3p2i_handle h, const float* partials_sum, float* out_act
 int m3p2i_comm_unique_id(void* out_id128 /* 128 bytes */);
 int m3p2i_comm_init(m3p2i_handle h, int rank, int nranks, const void* id128);
 
+/* Exchange over NVLink peer memory (replaces m3p2i_comm_init's two NCCL collectives per command): each rank's
+ * rollout kernel stores its discounted costs into every peer's HBM and the weighted-sum kernel does the same with the
+ * packed partial sums, so a sharded command stays at 3 kernel launches with no collective call.
+ * Every rank: m3p2i_peer_export -> exchange the descriptors through the host (torch.distributed all_gather_object,
+ * MPI, ...) -> m3p2i_peer_attach(all descriptors, indexed by rank) -> host barrier -> commands. Ranks may be processes
+ * (cudaIpc) or handles of one process. All ranks must issue the same sequence of commands. At most 8 ranks (one
+ * NVSwitch domain). A peer that stops delivering makes the next fetch fail with M3P2I_ERR_STATE instead of hanging. */
+typedef struct M3P2IPeerHandle {
+  unsigned char ipc[64];  /* cudaIpcMemHandle_t of the rank's mailbox */
+  int64_t pid;            /* exporting process */
+  uint64_t ptr;           /* device pointer, valid inside the exporting process */
+  uint64_t bytes;         /* mailbox size (must agree on all ranks) */
+  int32_t device;
+  int32_t reserved;
+} M3P2IPeerHandle;
+int m3p2i_peer_export(m3p2i_handle h, M3P2IPeerHandle* out);
+int m3p2i_peer_attach(m3p2i_handle h, int rank, int nranks, const M3P2IPeerHandle* all);
+
 #ifdef __cplusplus
 }
 #endif

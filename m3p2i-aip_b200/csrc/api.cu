@@ -1,6 +1,7 @@
 // api.cu — C ABI of libm3p2i_b200.so (include/m3p2i_b200.h): handle life cycle, host<->device staging, launch
 // sequencing of one planner tick, the IsaacGymWrapper-style sim facade, and the K-sharded multi-GPU path (NCCL).
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -113,6 +114,12 @@ struct M3P2IHandle_ {
   // multi-GPU
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  // exchange over peer memory (m3p2i_peer_export / m3p2i_peer_attach): layout in mailbox_layout()
+  float* mailbox = nullptr;                 // this rank's mailbox (cudaMalloc, exported with cudaIpc)
+  float* peer_box[kMaxPeers] = {nullptr};   // every rank's mailbox as mapped here ([rank] == mailbox)
+  bool peer_ipc[kMaxPeers] = {false};       // mapping came from cudaIpcOpenMemHandle (close it on destroy)
+  bool peer_on = false;
+  unsigned peer_epoch = 0;
 };
 
 namespace {
@@ -309,7 +316,48 @@ RolloutBufs make_rbufs(const H* h) {
   b.actions = h->actions.p; b.states = h->states.p; b.cost_h = h->cost_h.p; b.J = h->J.p; b.cost_sum = h->cost_sum.p;
   b.refs = nullptr;
   b.ref_flags = h->ref_flags.p;
+  memset(&b.peer, 0, sizeof(b.peer));
   return b;
+}
+
+// words of one parity of a mailbox: Jg[Kg] | part[kMaxPeers][np] | jflag[kMaxPeers] | pflag[kMaxPeers]
+struct MailboxLayout {
+  size_t np, off_part, off_jflag, off_pflag, stride;
+};
+MailboxLayout mailbox_layout(const H* h) {
+  MailboxLayout m;
+  const size_t Kg = ((size_t)h->cfg.num_samples_global + 31) / 32 * 32;
+  m.np = (6 * (size_t)h->cfg.horizon * h->cfg.nu + 1 + 31) / 32 * 32;
+  m.off_part = Kg;
+  m.off_jflag = m.off_part + kMaxPeers * m.np;
+  m.off_pflag = m.off_jflag + 32;
+  m.stride = m.off_pflag + 32;
+  return m;
+}
+// pointers of this command's parity; call once per command after ++peer_epoch
+void fill_peer(const H* h, PeerPush* push, PeerReduce* red) {
+  const MailboxLayout m = mailbox_layout(h);
+  const size_t par = (h->peer_epoch & 1u) * m.stride;
+  if (push) {
+    push->n = h->nranks; push->rank = h->rank; push->epoch = h->peer_epoch;
+    for (int r = 0; r < h->nranks; ++r) {
+      push->Jg[r] = h->peer_box[r] + par;
+      push->jflag[r] = reinterpret_cast<unsigned*>(h->peer_box[r] + par + m.off_jflag);
+    }
+    push->ticket = h->ref_flags.p + 3;
+  }
+  if (red) {
+    red->n = h->nranks; red->rank = h->rank; red->np = (int)m.np; red->epoch = h->peer_epoch;
+    red->spin_limit = 8u << 20;   // x (64 ns sleep + one L2 read): a few seconds
+    red->jflag_local = reinterpret_cast<const unsigned*>(h->mailbox + par + m.off_jflag);
+    red->part_local = h->mailbox + par + m.off_part;
+    red->pflag_local = reinterpret_cast<const unsigned*>(h->mailbox + par + m.off_pflag);
+    for (int r = 0; r < h->nranks; ++r) {
+      red->part[r] = h->peer_box[r] + par + m.off_part;
+      red->pflag[r] = reinterpret_cast<unsigned*>(h->peer_box[r] + par + m.off_pflag);
+    }
+    red->error = h->ref_flags.p + 4;
+  }
 }
 
 UpdateCfg make_ucfg(const H* h, int shift) {
@@ -328,7 +376,14 @@ UpdateBufs make_ubufs(const H* h) {
   b.cost_sum = h->cost_sum.p; b.partials = h->partials.p; b.seq = h->seq.p; b.filt = h->have_filt ? h->filt.p : nullptr;
   b.cost_total = h->cost_total.p; b.result = h->result.p; b.info = h->info.p;
   b.done_counter = h->ref_flags.p + 2;
+  memset(&b.peer, 0, sizeof(b.peer));
   return b;
+}
+
+// where the gathered discounted costs of the last command live
+const float* j_global_ptr(const H* h) {
+  if (h->peer_on && h->nranks > 1 && h->peer_epoch) return h->mailbox + (h->peer_epoch & 1u) * mailbox_layout(h).stride;
+  return h->J_global.p;
 }
 
 bool needs_refs(const H* h) { return h->cfg.env_type == M3P2I_ENV_PANDA && h->task == M3P2I_TASK_REACH; }
@@ -350,7 +405,7 @@ int upload_base(H* h) {
 }
 
 // phase 1: sample + rollout of the local shard; J of the local shard lands in h->J (and, single rank, J_global)
-int run_rollout(H* h, int* launches, const float* actions_in_dev) {
+int run_rollout(H* h, int* launches, const float* actions_in_dev, bool push_peers = false) {
   int rc = upload_base(h);
   if (rc) return rc;
   RolloutCfg c = make_rcfg(h);
@@ -368,6 +423,7 @@ int run_rollout(H* h, int* launches, const float* actions_in_dev) {
     h->ref_epoch += 64;   // > max horizon: flags of this launch run from epoch+1 to epoch+T
     c.epoch = h->ref_epoch;
   }
+  if (h->peer_on && push_peers) fill_peer(h, &b.peer, nullptr);
   launch_rollout(h->cfg.env_type, c, &h->pp, &h->qp, b, refs, h->stream, launches);
   CK(cudaGetLastError());
   if (h->env_alloc) h->env_live = true;
@@ -378,6 +434,10 @@ int run_update(H* h, int shift, int* launches, bool fuse_finish = false) {
   UpdateCfg u = make_ucfg(h, shift);
   u.fuse_finish = fuse_finish ? 1 : 0;
   UpdateBufs b = make_ubufs(h);
+  if (h->peer_on && fuse_finish && h->nranks > 1) {
+    fill_peer(h, nullptr, &b.peer);
+    b.J_global = h->mailbox + (h->peer_epoch & 1u) * mailbox_layout(h).stride;
+  }
   launch_stats(u, b, h->stream, launches);
   launch_wsum(u, b, h->stream, launches);
   CK(cudaGetLastError());
@@ -424,7 +484,11 @@ int fetch(H* h, float* out_action, float* out_cost_total, M3P2ICommandInfo* info
   CK(cudaMemcpyAsync(pi, h->info.p, sizeof(M3P2ICommandInfo), cudaMemcpyDeviceToHost, h->stream));
   float* pc = p + 2 * TN + sizeof(M3P2ICommandInfo) / sizeof(float) + 1;
   if (out_cost_total) CK(cudaMemcpyAsync(pc, h->cost_total.p, sizeof(float) * K, cudaMemcpyDeviceToHost, h->stream));
+  unsigned* perr = reinterpret_cast<unsigned*>(p + 2 * TN + sizeof(M3P2ICommandInfo) / sizeof(float));
+  *perr = 0u;
+  if (h->peer_on) CK(cudaMemcpyAsync(perr, h->ref_flags.p + 4, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (*perr) return fail(M3P2I_ERR_STATE, "peer exchange timed out: a rank did not deliver its costs / partial sums");
   if (out_action) memcpy(out_action, unfiltered ? p + TN : p, sizeof(float) * TN);
   if (out_cost_total) memcpy(out_cost_total, pc, sizeof(float) * K);
   const float kms = h->last_info.kernel_ms, rms = h->last_info.rollout_ms;
@@ -443,11 +507,13 @@ int command_device(H* h) {
   if (rc) return rc;
   int launches = 0;
   CK(cudaEventRecord(h->ev0, h->stream));
-  if ((rc = run_rollout(h, &launches, nullptr))) return rc;
+  const bool peers = h->peer_on && h->nranks > 1;   // exchange fused into the kernels over peer memory
+  if (peers) ++h->peer_epoch;
+  if ((rc = run_rollout(h, &launches, nullptr, peers))) return rc;
   CK(cudaEventRecord(h->evr, h->stream));
   h->have_evr = true;
-  if ((rc = gather_J(h))) return rc;
-  const bool fused = h->nranks == 1 || !h->comm;   // no exchange between the sums and the mean update
+  if (!peers && (rc = gather_J(h))) return rc;
+  const bool fused = peers || h->nranks == 1 || !h->comm;   // no host-visible exchange between sums and mean update
   if ((rc = run_update(h, 1, &launches, fused))) return rc;
   if (!fused) {
     if ((rc = reduce_partials(h))) return rc;
@@ -490,7 +556,7 @@ int m3p2i_abi_sizeof(const char* name) {
   if (!name) return -1;
 #define SZ(T) if (!strcmp(name, #T)) return (int)sizeof(T)
   SZ(M3P2IConfig); SZ(M3P2IBox); SZ(M3P2IBody); SZ(M3P2IPointScene); SZ(M3P2IPandaScene); SZ(M3P2IPlannerState);
-  SZ(M3P2ICommandInfo);
+  SZ(M3P2ICommandInfo); SZ(M3P2IPeerHandle);
 #undef SZ
   return -1;
 }
@@ -543,7 +609,8 @@ int m3p2i_create(const M3P2IConfig* cfg, int device, m3p2i_handle* out) {
   if (e == cudaSuccess) e = h->cost_total.alloc(K);
   if (e == cudaSuccess) e = h->result.alloc(2 * TN);
   if (e == cudaSuccess) e = h->refs.alloc(T);
-  if (e == cudaSuccess) e = h->ref_flags.alloc(4);   // [0,1] producer progress, [2] fused-update CTA counter
+  if (e == cudaSuccess) e = h->ref_flags.alloc(8);   // [0,1] producer progress, [2] fused-update CTA counter,
+                                                      // [3] peer-push ticket, [4] peer-wait error
   if (e == cudaSuccess) e = h->stats.alloc(1);
   if (e == cudaSuccess) e = h->info.alloc(1);
   if (e == cudaSuccess) {
@@ -568,6 +635,9 @@ void m3p2i_destroy(m3p2i_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (h->peer_ipc[r] && h->peer_box[r]) cudaIpcCloseMemHandle(h->peer_box[r]);
+  if (h->mailbox) cudaFree(h->mailbox);
   h->noise.release(); h->noise_row0.release(); h->seq.release(); h->actions_in.release(); h->base.release();
   h->env.release(); h->vel_target.release(); h->actions.release(); h->cost_h.release(); h->J.release();
   h->cost_sum.release(); h->J_global.release(); h->weights.release(); h->partials.release(); h->filt.release();
@@ -843,7 +913,7 @@ int m3p2i_get_buffer(m3p2i_handle h, int which, void** dev_ptr, size_t* bytes) {
     case M3P2I_BUF_ACTIONS: *dev_ptr = h->actions.p; *bytes = 4 * K * T * nu; break;
     case M3P2I_BUF_STATES: *dev_ptr = h->states.p; *bytes = 16 * K * T; break;
     case M3P2I_BUF_COST_HORIZON: *dev_ptr = h->cost_h.p; *bytes = 4 * K * T; break;
-    case M3P2I_BUF_COST_DISC: *dev_ptr = h->J_global.p; *bytes = 4 * Kg; break;
+    case M3P2I_BUF_COST_DISC: *dev_ptr = const_cast<float*>(j_global_ptr(h)); *bytes = 4 * Kg; break;
     case M3P2I_BUF_COST_SUM: *dev_ptr = h->cost_sum.p; *bytes = 4 * K; break;
     case M3P2I_BUF_WEIGHTS: *dev_ptr = h->weights.p; *bytes = 12 * Kg; break;
     case M3P2I_BUF_NOISE: *dev_ptr = h->have_noise ? h->noise.p : nullptr; *bytes = h->have_noise ? 4 * K * T * nu : 0; break;
@@ -862,7 +932,7 @@ int m3p2i_read_buffer(m3p2i_handle h, int which, float* out, size_t count) {
     case M3P2I_BUF_ACTIONS: src = h->actions.p; n = K * T * nu; rows = (int)(T * nu); cols = (int)K; break;
     case M3P2I_BUF_COST_HORIZON: src = h->cost_h.p; n = K * T; rows = (int)T; cols = (int)K; break;
     case M3P2I_BUF_STATES: src = reinterpret_cast<const float*>(h->states.p); n = K * T * 4; break;
-    case M3P2I_BUF_COST_DISC: src = h->J_global.p; n = Kg; break;
+    case M3P2I_BUF_COST_DISC: src = j_global_ptr(h); n = Kg; break;
     case M3P2I_BUF_COST_SUM: src = h->cost_sum.p; n = K; break;
     case M3P2I_BUF_WEIGHTS: src = h->weights.p; n = 3 * Kg; break;
     case M3P2I_BUF_NOISE: return m3p2i_get_noise(h, out);
@@ -1118,6 +1188,68 @@ int m3p2i_comm_init(m3p2i_handle h, int rank, int nranks, const void* id128) {
   ncclResult_t r = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
   if (r != ncclSuccess) return fail(M3P2I_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
   h->rank = rank; h->nranks = nranks;
+  h->peer_on = false;   // the NCCL collectives are the exchange from now on
+  return 0;
+}
+
+// ---------------------------------------------------------------- exchange over NVLink peer memory
+// Replaces the two NCCL collectives of a sharded command by stores into peer HBM issued from inside the rollout and
+// weighted-sum kernels (common.cuh, "exchange over NVLink peer memory"). Protocol: every rank calls
+// m3p2i_peer_export, the 80-byte descriptors are exchanged by the host (any transport), every rank calls
+// m3p2i_peer_attach with all of them, and a host barrier follows before the first command.
+int m3p2i_peer_export(m3p2i_handle h, M3P2IPeerHandle* out) {
+  if (!h || !out) return fail(M3P2I_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  const size_t bytes = 2 * mailbox_layout(h).stride * sizeof(float);
+  if (!h->mailbox) {
+    CK(cudaMalloc(&h->mailbox, bytes));
+    CK(cudaMemset(h->mailbox, 0, bytes));
+    CK(cudaDeviceSynchronize());
+  }
+  memset(out, 0, sizeof(*out));
+  cudaIpcMemHandle_t ipc;
+  static_assert(sizeof(ipc) == sizeof(out->ipc), "cudaIpcMemHandle_t is 64 bytes");
+  // same-process peers (several handles in one process) use the pointer; the IPC handle may be unavailable then
+  if (cudaIpcGetMemHandle(&ipc, h->mailbox) == cudaSuccess) memcpy(out->ipc, &ipc, sizeof(ipc));
+  else cudaGetLastError();
+  out->pid = (int64_t)getpid();
+  out->ptr = (uint64_t)reinterpret_cast<uintptr_t>(h->mailbox);
+  out->device = h->device;
+  out->bytes = (uint64_t)bytes;
+  return 0;
+}
+
+int m3p2i_peer_attach(m3p2i_handle h, int rank, int nranks, const M3P2IPeerHandle* all) {
+  if (!h || !all || nranks < 1 || nranks > kMaxPeers || rank < 0 || rank >= nranks)
+    return fail(M3P2I_ERR_ARG, "bad argument (at most 8 ranks)");
+  if (!h->mailbox) return fail(M3P2I_ERR_STATE, "m3p2i_peer_export has not been called on this handle");
+  if ((long long)h->cfg.num_samples * nranks != h->cfg.num_samples_global || h->cfg.sample_offset != rank * h->cfg.num_samples)
+    return fail(M3P2I_ERR_ARG, "K must be split evenly: num_samples * nranks == num_samples_global, offset = rank * num_samples");
+  CK(cudaSetDevice(h->device));
+  const uint64_t bytes = 2 * mailbox_layout(h).stride * sizeof(float);
+  for (int r = 0; r < nranks; ++r) {
+    if (all[r].bytes != bytes) return fail(M3P2I_ERR_ARG, "peer mailbox size differs: K_global, horizon and nu must match on all ranks");
+    if (r == rank) { h->peer_box[r] = h->mailbox; continue; }
+    if (all[r].pid == (int64_t)getpid()) {
+      if (all[r].device != h->device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, h->device, all[r].device));
+        if (!can) return fail(M3P2I_ERR_STATE, "no peer access between the devices of two handles");
+        cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        cudaGetLastError();
+      }
+      h->peer_box[r] = reinterpret_cast<float*>(static_cast<uintptr_t>(all[r].ptr));
+    } else {
+      cudaIpcMemHandle_t ipc;
+      memcpy(&ipc, all[r].ipc, sizeof(ipc));
+      void* p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+      h->peer_box[r] = static_cast<float*>(p);
+      h->peer_ipc[r] = true;
+    }
+  }
+  h->rank = rank; h->nranks = nranks; h->peer_on = true; h->peer_epoch = 0;
   return 0;
 }
 

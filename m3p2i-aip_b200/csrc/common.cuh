@@ -72,6 +72,36 @@ struct PandaRef {
   int sel_axis;
 };
 
+// ------------------------------------------------------------------ exchange over NVLink peer memory (sharded K)
+// Every rank owns a MAILBOX in its own HBM that all peers map (cudaIpc): two parities of
+//   Jg[Kg] | part[n][NP] | jflag[n] | pflag[n]
+// The rollout kernel of rank r stores its discounted costs straight into Jg[offset_r ...] of EVERY mailbox (its own
+// included) and the last sample to finish raises jflag[r] there: rollout + all-gather in one kernel. The weighted-sum
+// kernel's last CTA does the same with the packed partial sums (part[r], pflag[r]) and then adds the n boxes of its
+// own mailbox in rank order: sums + all-reduce + mean update in one kernel, bitwise identical on every rank.
+// Flags carry the command's epoch; parity = epoch & 1 (a rank can be at most one command ahead of a peer).
+constexpr int kMaxPeers = 8;
+
+struct PeerPush {          // rollout side
+  int n, rank;             // n == 0: no peers (single rank, or NCCL / host exchange)
+  unsigned epoch;
+  float* Jg[kMaxPeers];        // Jg of this parity in the mailbox of rank i
+  unsigned* jflag[kMaxPeers];  // jflag[0..n) of this parity in the mailbox of rank i
+  unsigned* ticket;            // local: number of samples of this launch whose J has been pushed
+};
+
+struct PeerReduce {        // update side
+  int n, rank, np;         // np = padded length of one partials box
+  unsigned epoch;
+  unsigned spin_limit;     // give up (set *error) after this many polls of a flag: a dead peer must not hang the GPU
+  const unsigned* jflag_local;   // [n] this parity, local mailbox (k_stats waits for them)
+  const float* part_local;       // [n][np] this parity, local mailbox
+  const unsigned* pflag_local;   // [n]
+  float* part[kMaxPeers];        // part[0..n) of this parity in the mailbox of rank i
+  unsigned* pflag[kMaxPeers];
+  unsigned* error;               // local: set to 1 when a wait gave up
+};
+
 struct RolloutBufs {
   const float* noise;      // [T][nu][K] (table mode) or nullptr
   const float* noise_row0; // [T][nu] noise of GLOBAL sample 0 for shards that do not own it, or nullptr
@@ -87,6 +117,7 @@ struct RolloutBufs {
   float* cost_sum;         // [K]  undiscounted sum
   PandaRef* refs;          // [T] rows 0 / Kg/2 of the batch, published step by step by the producer CTA
   unsigned* ref_flags;     // [2] progress counters of the two producers (cube position, cube axis)
+  PeerPush peer;
 };
 
 // ------------------------------------------------------------------ small math

@@ -129,6 +129,38 @@ DEV PandaRef ref_wait(const RolloutBufs& b, int t, unsigned epoch, bool two) {
   return out;
 }
 
+// ------------------------------------------------------------------ all-gather of J fused into the rollout
+// Called by the one thread that owns sample k once its rollout is complete. System-scope fences order the remote
+// stores before the ticket and the ticket before the flags, so a peer that sees jflag == epoch sees every J.
+DEV void push_J(const PeerPush& p, int K, int offset, int k, float J) {
+  for (int r = 0; r < p.n; ++r) p.Jg[r][offset + k] = J;
+  __threadfence_system();
+  if (atomicAdd(p.ticket, 1u) == (unsigned)K - 1u) {
+    *p.ticket = 0u;   // the next launch on this stream starts from zero
+    __threadfence_system();
+    for (int r = 0; r < p.n; ++r) *(volatile unsigned*)(p.jflag[r] + p.rank) = p.epoch;
+  }
+}
+DEV void publish_J(const RolloutBufs& b, const RolloutCfg& c, int k, float J) {
+  b.J[k] = J;
+  if (b.peer.n) push_J(b.peer, c.K, c.offset, k, J);
+}
+
+// Threads 0..n-1 of the CTA poll one flag each until it reaches `epoch`; bounded, so that a peer that died cannot
+// hang this GPU (the command then reports M3P2I_ERR_STATE through *error).
+DEV void wait_flags(const unsigned* flags, int n, unsigned epoch, unsigned limit, unsigned* error) {
+  if ((int)threadIdx.x < n) {
+    const volatile unsigned* f = flags + threadIdx.x;
+    unsigned polls = 0;
+    while ((int)(*f - epoch) < 0) {
+      if (++polls > limit) { *error = 1u; break; }
+      __nanosleep(64);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------ fused rollout
 // noise -> perturbation -> clamp -> T x (dynamics step, task cost, discounted accumulate) with per-step stores of
 // the action planes, the float4 state row and the cost (mppi.py:275-332 with reactive_tamp.py:63-73 inlined).
@@ -183,8 +215,8 @@ k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename
     b.states[(size_t)t * K + k] = e.state_row();
     b.cost_h[(size_t)t * K + k] = cost;
   }
-  b.J[k] = J;
   b.cost_sum[k] = run;
+  publish_J(b, c, k, J);
   if (c.store_env) {
     e.store(b.env, K, k);
 #pragma unroll
@@ -345,6 +377,8 @@ __global__ void __launch_bounds__(kStatsBlock) k_stats(const UpdateCfg u, const 
   __shared__ int shi[32];
   const int Kg = u.Kg, half = Kg / 2;
   const float* J = b.J_global;
+  // sharded over peer memory: J_global is the local mailbox; every rank's slice has landed once its flag is up
+  if (b.peer.n) wait_flags(b.peer.jflag_local, b.peer.n, b.peer.epoch, b.peer.spin_limit, b.peer.error);
   Stats* S = b.stats;
   const int nsets = u.multi_modal ? 3 : 1;
   int iters = 0;
@@ -466,6 +500,29 @@ __global__ void __launch_bounds__(kSumBlock) k_wsum(const UpdateCfg u, const Upd
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  if (b.peer.n) {
+    // all-reduce over peer memory: this rank's packed partial sums go into box [rank] of every mailbox ...
+    const PeerReduce& p = b.peer;
+    const int NP = 6 * TN + 1;
+    const volatile float* mine = b.partials;
+    for (int i = threadIdx.x; i < NP; i += kSumBlock) {
+      const float v = mine[i];
+      for (int r = 0; r < p.n; ++r) p.part[r][(size_t)p.rank * p.np + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int r = 0; r < p.n; ++r) *(volatile unsigned*)(p.pflag[r] + p.rank) = p.epoch;
+    // ... and the n boxes of the own mailbox are added in rank order (the same bits on every rank)
+    wait_flags(p.pflag_local, p.n, p.epoch, p.spin_limit, p.error);
+    for (int i = threadIdx.x; i < NP; i += kSumBlock) {
+      float a = 0.0f;
+      for (int r = 0; r < p.n; ++r) a += __ldcg(p.part_local + (size_t)r * p.np + i);
+      b.partials[i] = a;
+    }
+    __threadfence();
+    __syncthreads();
+  }
   finish_body(u, b, smean);
 }
 

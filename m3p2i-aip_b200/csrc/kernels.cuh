@@ -36,6 +36,7 @@ struct UpdateBufs {
   float* result;           // [T*nu] filtered action, followed by [T*nu] unfiltered mean
   M3P2ICommandInfo* info;  // device copy
   unsigned* done_counter;  // CTA completion counter of the fused wsum + finish launch
+  PeerReduce peer;
 };
 
 void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp,

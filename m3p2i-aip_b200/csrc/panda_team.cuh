@@ -671,7 +671,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     }
   }
   if (producer) return;
-  if (writer) { b.J[k] = J; b.cost_sum[k] = run; }
+  if (writer) { b.cost_sum[k] = run; publish_J(b, c, k, J); }
   if (c.store_env && valid) {
     e.store(b.env, K, k, t);
     if (writer) {

@@ -87,7 +87,12 @@ class CommandInfo(C.Structure):
     ]
 
 
-STRUCTS = {"M3P2IConfig": Config, "M3P2IBox": Box, "M3P2IBody": Body, "M3P2IPointScene": PointScene,
+class PeerHandle(C.Structure):
+    _fields_ = [("ipc", C.c_ubyte * 64), ("pid", C.c_int64), ("ptr", C.c_uint64), ("bytes", C.c_uint64),
+                ("device", i32), ("reserved", i32)]
+
+
+STRUCTS = {"M3P2IPeerHandle": PeerHandle, "M3P2IConfig": Config, "M3P2IBox": Box, "M3P2IBody": Body, "M3P2IPointScene": PointScene,
            "M3P2IPandaScene": PandaScene, "M3P2IPlannerState": PlannerState, "M3P2ICommandInfo": CommandInfo}
 
 fp = C.POINTER(f32)
@@ -134,6 +139,8 @@ PROTOTYPES = {
     "m3p2i_phase_finish": (C.c_int, [vp, fp, fp, fp, C.POINTER(CommandInfo)]),
     "m3p2i_comm_unique_id": (C.c_int, [vp]),
     "m3p2i_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "m3p2i_peer_export": (C.c_int, [vp, C.POINTER(PeerHandle)]),
+    "m3p2i_peer_attach": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(PeerHandle)]),
     "m3p2i_set_stream": (C.c_int, [vp, vp]),
 }
 

@@ -224,6 +224,17 @@ class NativePlanner:
         buf = (C.c_char * 128).from_buffer_copy(unique_id)
         self._ck(self.fn["m3p2i_comm_init"](self.h, rank, nranks, C.cast(buf, A.vp)), "m3p2i_comm_init")
 
+    def peer_export(self):
+        """This rank's mailbox descriptor (bytes) for the exchange over NVLink peer memory (m3p2i_peer_export)."""
+        ph = A.PeerHandle()
+        self._ck(self.fn["m3p2i_peer_export"](self.h, C.byref(ph)), "m3p2i_peer_export")
+        return bytes(ph)
+
+    def peer_attach(self, rank, nranks, descriptors):
+        """descriptors: the peer_export() bytes of every rank, indexed by rank. Follow with a host barrier."""
+        arr = (A.PeerHandle * nranks)(*[A.PeerHandle.from_buffer_copy(d) for d in descriptors])
+        self._ck(self.fn["m3p2i_peer_attach"](self.h, rank, nranks, arr), "m3p2i_peer_attach")
+
     # ---------------------------------------------------------------- persistent K-env sim facade
     def sim_reset(self):
         self._ck(self.fn["m3p2i_sim_reset"](self.h), "m3p2i_sim_reset")

@@ -20,6 +20,27 @@ def shard_bounds(K_global, rank, world):
     return Kl, rank * Kl
 
 
+def attach_peers(backend, group=None):
+    """Switch a sharded NativePlanner to the exchange over NVLink peer memory: descriptors travel through
+    torch.distributed (any backend), the data path afterwards is stores into peer HBM issued by the kernels
+    themselves (include/m3p2i_b200.h, m3p2i_peer_*). One process per GPU. Raises on EVERY rank if any rank failed to map
+    its peers (the caller can then fall back to m3p2i_comm_init together)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = backend.peer_export()
+    every = [None] * world
+    dist.all_gather_object(every, mine, group=group)
+    err = None
+    try:
+        backend.peer_attach(rank, world, every)
+    except Exception as exc:  # e.g. cudaIpc not permitted: all ranks must learn of it, or the next collective hangs
+        err = repr(exc)
+    errs = [None] * world
+    dist.all_gather_object(errs, err, group=group)    # agreement + barrier: no rank starts before all have attached
+    bad = [f"rank {r}: {e}" for r, e in enumerate(errs) if e is not None]
+    if bad:
+        raise RuntimeError("peer-memory exchange unavailable (" + "; ".join(bad) + ")")
+
+
 class ShardedPlanner:
     def __init__(self, backend, group=None, device="cpu"):
         self.b = backend

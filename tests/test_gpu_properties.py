@@ -121,6 +121,51 @@ def test_shard_invariance(task, mm):
     full.close()
 
 
+@pytest.mark.parametrize("task,mm,nshard", [("pick", False, 2), ("reach", True, 2), ("pick", False, 4)])
+def test_peer_memory_exchange_matches_unsharded(task, mm, nshard):
+    """The exchange fused into the kernels (m3p2i_peer_export / m3p2i_peer_attach: the rollout kernel stores J into
+    every rank's mailbox, the weighted-sum kernel's last CTA pushes and reduces the partial sums) with the ranks as
+    handles of ONE process on ONE GPU -- the same kernels and flag protocol as one process per GPU over NVLink, where
+    only the mapping of the mailboxes (cudaIpc) differs. Three ticks; every rank must report the unsharded action
+    and its slice of the unsharded per-sample costs, and all ranks must agree bit for bit."""
+    K, T = 2048, 16
+    _, full, _ = _c4(K, T, task, mm)
+    Kl = K // nshard
+    shards = [_c4(K, T, task, mm, K_local=Kl, offset=r * Kl)[1] for r in range(nshard)]
+    desc = [s.peer_export() for s in shards]
+    for r, s in enumerate(shards):
+        s.peer_attach(r, nshard, desc)
+    for tick in range(3):
+        a_full, c_full, info_full = full.command()
+        a_full, c_full = a_full.copy(), c_full.copy()
+        J_full = full.read_buffer(A.BUF_COST_DISC)
+        for s in shards:
+            s.command_resident()          # asynchronous: every rank's kernels must be in flight before any fetch
+        outs = [(a.copy(), c.copy()) for a, c in (s.fetch_result() for s in shards)]
+        for r, (a, c) in enumerate(outs):
+            assert np.array_equal(shards[r].read_buffer(A.BUF_COST_DISC), J_full), f"tick {tick} rank {r}: gathered J"
+            assert_close(a, a_full, 1e-5, 1e-6, f"tick {tick} action rank {r}/{nshard}")
+            assert_close(c, c_full[r * Kl:(r + 1) * Kl], 1e-6, 1e-4, f"tick {tick} cost_total rank {r}/{nshard}")
+            assert np.array_equal(a, outs[0][0]), f"tick {tick}: rank {r} and rank 0 disagree"
+    for s in shards:
+        s.close()
+    full.close()
+
+
+def test_peer_exchange_reports_a_missing_rank():
+    """A rank that never delivers must not hang the GPU: the waits are bounded and the fetch fails loudly."""
+    K, T = 256, 12
+    shards = [_c4(K, T, "pick", False, K_local=K // 2, offset=r * (K // 2))[1] for r in range(2)]
+    desc = [s.peer_export() for s in shards]
+    for r, s in enumerate(shards):
+        s.peer_attach(r, 2, desc)
+    shards[0].command_resident()          # rank 1 never runs
+    with pytest.raises(native.NativeError, match="peer exchange timed out"):
+        shards[0].fetch_result()
+    for s in shards:
+        s.close()
+
+
 def test_table_and_philox_agree():
     """Feeding the dumped Philox table back in table mode gives the same rollout."""
     _, p, _ = _c4(1024, 16)

@@ -1,5 +1,7 @@
-"""Run under torchrun with N ranks: K sharded over N GPUs through m3p2i_comm_init (NCCL all-gather of the
-discounted costs + all-reduce of the packed partial sums on the kernel stream) must reproduce the unsharded command.
+"""Run under torchrun with N ranks: K sharded over N GPUs must reproduce the unsharded command, with either exchange:
+    EXCHANGE=nccl  m3p2i_comm_init: NCCL all-gather of the discounted costs + all-reduce of the packed partial sums
+    EXCHANGE=peer  m3p2i_peer_export / m3p2i_peer_attach: stores into peer HBM (cudaIpc over NVLink) issued by the
+                   rollout and weighted-sum kernels themselves, no collective call (default)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/nccl_check.py"""
 import os
 import sys
@@ -11,7 +13,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "m3p2i-aip_b200"))
 sys.path.insert(0, ROOT)
-from m3p2i_b200 import _abi as A, native, scene as S  # noqa: E402
+from m3p2i_b200 import _abi as A, native, scene as S, sharded  # noqa: E402
 import bench  # noqa: E402
 
 
@@ -33,13 +35,17 @@ def main():
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     ok = True
+    exchange = os.environ.get("EXCHANGE", "peer")
     for task, mm in (("pick", False), ("reach", True)):
         K, T = 1024 * world, 16
         Kl = K // world
         p = make(task, mm, K, T, Kl, rank * Kl, lr)
-        uid = [native.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        p.comm_init(rank, world, uid[0])
+        if exchange == "peer":
+            sharded.attach_peers(p)
+        else:
+            uid = [native.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            p.comm_init(rank, world, uid[0])
         outs = []
         for _ in range(3):
             a, c, info = p.command()
@@ -58,7 +64,7 @@ def main():
         p.close()
         dist.barrier()
     if rank == 0:
-        print("NCCL sharded command:", "PASS" if ok else "FAIL", flush=True)
+        print(f"sharded command over {world} GPUs, exchange={exchange}:", "PASS" if ok else "FAIL", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
