@@ -1195,7 +1195,7 @@ int m3p2i_comm_init(m3p2i_handle h, int rank, int nranks, const void* id128) {
 // ---------------------------------------------------------------- exchange over NVLink peer memory
 // Replaces the two NCCL collectives of a sharded command by stores into peer HBM issued from inside the rollout and
 // weighted-sum kernels (common.cuh, "exchange over NVLink peer memory"). Protocol: every rank calls
-// m3p2i_peer_export, the 80-byte descriptors are exchanged by the host (any transport), every rank calls
+// m3p2i_peer_export, the 96-byte descriptors are exchanged by the host (any transport), every rank calls
 // m3p2i_peer_attach with all of them, and a host barrier follows before the first command.
 int m3p2i_peer_export(m3p2i_handle h, M3P2IPeerHandle* out) {
   if (!h || !out) return fail(M3P2I_ERR_ARG, "null argument");
