@@ -186,7 +186,10 @@ typedef struct M3P2IPandaScene {
   int32_t idx_shelf;
   int32_t link_sweeps;   /* Gauss-Seidel sweeps over the finger/hand-cube contacts inside each solver pass (<= 0: 4):
                             the finger - cube - finger chain of a grasp needs them to settle within a sub-step */
-  int32_t reserved;
+  int32_t report_cube_contacts; /* 1: the contact force reported for the table / shelf stand also contains the cubes
+                                   resting or sliding on them; 0 (default): only the robot's links count. The
+                                   collision cost (cost_functions.py:158-169) is about the ROBOT hitting the furniture,
+                                   and with 1 every rollout that slides cubeA on the table pays it */
   M3P2IBody cube_a;      /* 5_cubeA.yaml */
   M3P2IBody cube_b;      /* 6_cubeB.yaml */
   M3P2IBox statics[M3P2I_MAX_STATIC];

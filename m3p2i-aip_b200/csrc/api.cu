@@ -178,6 +178,7 @@ void build_panda_params(H* h) {
   p.contact_margin = s.contact_margin; p.baumgarte = s.baumgarte; p.slop = s.slop; p.max_corr_vel = s.max_corr_vel;
   p.penalty_stiffness = s.penalty_stiffness;
   p.link_sweeps = s.link_sweeps > 0 ? s.link_sweeps : 4;
+  p.report_cube = s.report_cube_contacts ? 1 : 0;
   const M3P2IBody* cb[2] = {&s.cube_a, &s.cube_b};
   for (int i = 0; i < 2; ++i) {
     memcpy(p.cube_half[i], cb[i]->half, 12);

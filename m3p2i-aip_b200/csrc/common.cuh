@@ -44,7 +44,7 @@ struct PandaParams {
   float finger_half[3], finger_center[3], hand_half[3], hand_center[3];
   float contact_margin, baumgarte, slop, max_corr_vel, penalty_stiffness;
   float cube_half[2][3], cube_mass[2], cube_inertia[2], cube_mu[2];
-  int n_static, idx_table, idx_shelf, link_sweeps;
+  int n_static, idx_table, idx_shelf, link_sweeps, report_cube;
   Static3 st[kMaxStatic];
 };
 

@@ -471,8 +471,8 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
             accS = accS - solve_cube_static(C[i].v, C[i].w, C[i].im, C[i].ii, C[i].x, n, depth, pt, mu, h, P);
           }
           if (p == 0) hit[i] |= (unsigned long long)found << (8 * k);
-          if (k == P.idx_table) imp_table = imp_table + accS;
-          if (k == P.idx_shelf) imp_shelf = imp_shelf + accS;
+          if (k == P.idx_table && P.report_cube) imp_table = imp_table + accS;
+          if (k == P.idx_shelf && P.report_cube) imp_shelf = imp_shelf + accS;
           if (i == 1) imp_cubeb = imp_cubeb - accS;
         }
       box_vs_box3<true>(C[0], cbox[0], C[1], cbox[1], 0.5f * (P.cube_mu[0] + P.cube_mu[1]), h, P, imp_cubeb);

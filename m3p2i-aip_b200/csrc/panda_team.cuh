@@ -509,8 +509,8 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
           got = got + apply_static_hits<G>(sh, r, t.group_base, v, w, im, ii, mu);
         }
         // impulses received by the fixed box = -(impulses on the cube)
-        if (ks == P.idx_table) imp_table = imp_table - got;
-        if (ks == P.idx_shelf) imp_shelf = imp_shelf - got;
+        if (ks == P.idx_table && P.report_cube) imp_table = imp_table - got;
+        if (ks == P.idx_shelf && P.report_cube) imp_shelf = imp_shelf - got;
         if (g == 1) imp_cubeb = imp_cubeb + got;
       }
       // (b) cubeA against cubeB, both ways; every lane of the team applies every impulse to replicas of both cubes

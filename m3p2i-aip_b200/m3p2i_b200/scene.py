@@ -197,6 +197,11 @@ def build_point_scene(actors=None):
     return s
 
 
+# field -> value applied to every M3P2IPandaScene built afterwards (solver experiments, tests that need the physical
+# table forces: {"report_cube_contacts": 1}, {"link_sweeps": 1}, ...)
+PANDA_SCENE_OVERRIDES = {}
+
+
 def build_panda_scene(actors=None):
     actors = actors or _panda_actors()
     robot = [a for a in actors if a.type == "robot"][-1]
@@ -223,6 +228,7 @@ def build_panda_scene(actors=None):
     s.max_corr_vel = 0.5
     s.penalty_stiffness = 2000.0
     s.link_sweeps = 4
+    s.report_cube_contacts = 0
     s.n_actors = len(actors)
     s.idx_table = -1
     s.idx_shelf = -1
@@ -245,6 +251,8 @@ def build_panda_scene(actors=None):
                 s.idx_shelf = n
             n += 1
     s.n_static = n
+    for key, value in PANDA_SCENE_OVERRIDES.items():
+        setattr(s, key, value)
     return s
 
 

@@ -407,8 +407,8 @@ static inline void o_panda_step(OPandaEnv* e, const M3P2IPandaScene* sc, const M
           OSolv3 S;
           memset(&S, 0, sizeof(S));
           memcpy(S.x, sb.c, 12);
-          if (k == sc->idx_table) S.acc = imp_table;
-          if (k == sc->idx_shelf) S.acc = imp_shelf;
+          if (k == sc->idx_table && sc->report_cube_contacts) S.acc = imp_table;
+          if (k == sc->idx_shelf && sc->report_cube_contacts) S.acc = imp_shelf;
           o_box_vs_box3(&C[i], &cbox[i], &S, &sb, 0.5f * (bp[i]->mu + sc->statics[k].mu), h, sc, 0);
         }
       o_box_vs_box3(&C[0], &cbox[0], &C[1], &cbox[1], 0.5f * (bp[0]->mu + bp[1]->mu), h, sc, 1);
