@@ -334,7 +334,8 @@ int m3p2i_comm_init(m3p2i_handle h, int rank, int nranks, const void* id128);
  * Every rank: m3p2i_peer_export -> exchange the descriptors through the host (torch.distributed all_gather_object,
  * MPI, ...) -> m3p2i_peer_attach(all descriptors, indexed by rank) -> host barrier -> commands. Ranks may be processes
  * (cudaIpc) or handles of one process. All ranks must issue the same sequence of commands. At most 8 ranks (one
- * NVSwitch domain). A peer that stops delivering makes the next fetch fail with M3P2I_ERR_STATE instead of hanging. */
+ * NVSwitch domain). A peer that stops delivering makes the next fetch fail with M3P2I_ERR_STATE instead of hanging:
+ * waits inside the kernels give up after M3P2I_PEER_TIMEOUT_MS (environment, read at attach; default 30000). */
 typedef struct M3P2IPeerHandle {
   unsigned char ipc[64];  /* cudaIpcMemHandle_t of the rank's mailbox */
   int64_t pid;            /* exporting process */

@@ -120,6 +120,7 @@ struct M3P2IHandle_ {
   bool peer_ipc[kMaxPeers] = {false};       // mapping came from cudaIpcOpenMemHandle (close it on destroy)
   bool peer_on = false;
   unsigned peer_epoch = 0;
+  unsigned peer_timeout_ms = 30000;   // M3P2I_PEER_TIMEOUT_MS at attach time
 };
 
 namespace {
@@ -349,7 +350,7 @@ void fill_peer(const H* h, PeerPush* push, PeerReduce* red) {
   }
   if (red) {
     red->n = h->nranks; red->rank = h->rank; red->np = (int)m.np; red->epoch = h->peer_epoch;
-    red->spin_limit = 8u << 20;   // x (64 ns sleep + one L2 read): a few seconds
+    red->timeout_ms = h->peer_timeout_ms;
     red->jflag_local = reinterpret_cast<const unsigned*>(h->mailbox + par + m.off_jflag);
     red->part_local = h->mailbox + par + m.off_part;
     red->pflag_local = reinterpret_cast<const unsigned*>(h->mailbox + par + m.off_pflag);
@@ -1250,6 +1251,7 @@ int m3p2i_peer_attach(m3p2i_handle h, int rank, int nranks, const M3P2IPeerHandl
       h->peer_ipc[r] = true;
     }
   }
+  if (const char* e = getenv("M3P2I_PEER_TIMEOUT_MS")) h->peer_timeout_ms = (unsigned)std::max(1, atoi(e));
   h->rank = rank; h->nranks = nranks; h->peer_on = true; h->peer_epoch = 0;
   return 0;
 }

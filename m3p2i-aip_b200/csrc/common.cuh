@@ -93,7 +93,7 @@ struct PeerPush {          // rollout side
 struct PeerReduce {        // update side
   int n, rank, np;         // np = padded length of one partials box
   unsigned epoch;
-  unsigned spin_limit;     // give up (set *error) after this many polls of a flag: a dead peer must not hang the GPU
+  unsigned timeout_ms;     // give up (set *error) after waiting this long for a flag: a dead peer must not hang the GPU
   const unsigned* jflag_local;   // [n] this parity, local mailbox (k_stats waits for them)
   const float* part_local;       // [n][np] this parity, local mailbox
   const unsigned* pflag_local;   // [n]

@@ -148,12 +148,18 @@ DEV void publish_J(const RolloutBufs& b, const RolloutCfg& c, int k, float J) {
 
 // Threads 0..n-1 of the CTA poll one flag each until it reaches `epoch`; bounded, so that a peer that died cannot
 // hang this GPU (the command then reports M3P2I_ERR_STATE through *error).
-DEV void wait_flags(const unsigned* flags, int n, unsigned epoch, unsigned limit, unsigned* error) {
+DEV unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+DEV void wait_flags(const unsigned* flags, int n, unsigned epoch, unsigned timeout_ms, unsigned* error) {
   if ((int)threadIdx.x < n) {
     const volatile unsigned* f = flags + threadIdx.x;
+    const unsigned long long t0 = global_ns(), limit = (unsigned long long)timeout_ms * 1000000ull;
     unsigned polls = 0;
     while ((int)(*f - epoch) < 0) {
-      if (++polls > limit) { *error = 1u; break; }
+      if ((++polls & 1023u) == 0u && global_ns() - t0 > limit) { *error = 1u; break; }
       __nanosleep(64);
     }
   }
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(kStatsBlock) k_stats(const UpdateCfg u, const 
   const int Kg = u.Kg, half = Kg / 2;
   const float* J = b.J_global;
   // sharded over peer memory: J_global is the local mailbox; every rank's slice has landed once its flag is up
-  if (b.peer.n) wait_flags(b.peer.jflag_local, b.peer.n, b.peer.epoch, b.peer.spin_limit, b.peer.error);
+  if (b.peer.n) wait_flags(b.peer.jflag_local, b.peer.n, b.peer.epoch, b.peer.timeout_ms, b.peer.error);
   Stats* S = b.stats;
   const int nsets = u.multi_modal ? 3 : 1;
   int iters = 0;
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(kSumBlock) k_wsum(const UpdateCfg u, const Upd
     if (threadIdx.x == 0)
       for (int r = 0; r < p.n; ++r) *(volatile unsigned*)(p.pflag[r] + p.rank) = p.epoch;
     // ... and the n boxes of the own mailbox are added in rank order (the same bits on every rank)
-    wait_flags(p.pflag_local, p.n, p.epoch, p.spin_limit, p.error);
+    wait_flags(p.pflag_local, p.n, p.epoch, p.timeout_ms, p.error);
     for (int i = threadIdx.x; i < NP; i += kSumBlock) {
       float a = 0.0f;
       for (int r = 0; r < p.n; ++r) a += __ldcg(p.part_local + (size_t)r * p.np + i);

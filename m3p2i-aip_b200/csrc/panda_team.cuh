@@ -273,14 +273,8 @@ DEV V3 apply_link_hits(const LinkHit& s, unsigned hb, int src0, bool mine, V3 ax
   return acc;
 }
 
-// hand pose + twist; sin/cos of joint j are computed by lane j of the team (one sincosf site) and broadcast
-DEV void team_fk(const PandaParams& P, const float* q, const float* qd, const TeamLane& t, Hand& H) {
-  const int j = min(t.tl, 6);
-  float qj = q[0];
-#pragma unroll
-  for (int i = 1; i < 7; ++i) { if (j == i) qj = q[i]; }
-  float snj, csj;
-  sincosf(qj, &snj, &csj);
+// hand pose + twist from the sines / cosines and speeds of the seven arm joints (the arithmetic of panda_hand)
+DEV void fk_from_sincos(const PandaParams& P, const float* sn, const float* cs, const float* qd, Hand& H) {
   V3 p = mk(P.base[0], P.base[1], P.base[2]);
   M33 R = {mk(1, 0, 0), mk(0, 1, 0), mk(0, 0, 1)};
   V3 v = mk(0, 0, 0), w = mk(0, 0, 0);
@@ -290,7 +284,6 @@ DEV void team_fk(const PandaParams& P, const float* q, const float* qd, const Te
   constexpr int ROLL[7] = {0, -1, 1, 1, -1, 1, 1};
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
-    const float sn = __shfl_sync(kFull, snj, t.team_base + i), cs = __shfl_sync(kFull, csj, t.team_base + i);
     const V3 d = mul(R, mk(X[i], Y[i], Z[i]));
     v = v + cross(w, d);
     p = p + d;
@@ -298,8 +291,8 @@ DEV void team_fk(const PandaParams& P, const float* q, const float* qd, const Te
     if (ROLL[i] == -1) { const V3 c1 = R.cy; R.cy = -R.cz; R.cz = c1; }
     w = w + qd[i] * R.cz;
     const V3 c0 = R.cx, c1 = R.cy;
-    R.cx = cs * c0 + sn * c1;
-    R.cy = cs * c1 - sn * c0;
+    R.cx = cs[i] * c0 + sn[i] * c1;
+    R.cy = cs[i] * c1 - sn[i] * c0;
   }
   const V3 d = kHandZ * R.cz;
   v = v + cross(w, d);
@@ -332,11 +325,25 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
   if (c.env_live && k >= 0) e.load(b.env, K, k, g);
   else e.load(b.base, 1, 0, g);
   float run = 0.0f, J = 0.0f, gam = 1.0f;
-  float u[NU];
-#pragma unroll
-  for (int d = 0; d < NU; ++d) u[d] = 0.0f;
   // group-partial impulse sums (identical in the lanes of a group), lane-partial penalty sums, per step
   V3 imp_table = mk(0, 0, 0), imp_shelf = mk(0, 0, 0), imp_cubeb = mk(0, 0, 0), pen = mk(0, 0, 0);
+
+  // ---- the arm runs ahead of the contacts. The seven arm joints are velocity-tracked and no contact acts on them,
+  // so their trajectory (and the hand pose) depends on the sampled actions only. Every TM iterations the team
+  // advances the arm TM sub-steps at once: lane j owns joint j (drive, limits, integration, one sincosf site), its
+  // (sin, cos, speed) are broadcast, and lane l keeps the snapshot of iteration blk0 + l and runs ONE forward
+  // kinematics for it. Inside the block an iteration then fetches its hand pose with 18 shuffles instead of
+  // recomputing the kinematic chain in every lane, and the action of a step is drawn once per lane per block.
+  const int jo = min(t.tl, 6);   // own arm joint (lanes 7.. shadow joint 6, their results are never read)
+  float qo = e.q[0], vo = e.qd[0];
+#pragma unroll
+  for (int i = 1; i < 7; ++i) { if (jo == i) { qo = e.q[i]; vo = e.qd[i]; } }
+  const float lo_o = P.q_lower[jo], up_o = P.q_upper[jo], vl_o = P.qd_limit[jo], ef_o = P.effort[jo];
+  Hand Hl;          // hand pose + twist of iteration blk0 + t.tl
+  float ul[NU];     // action of the step of iteration blk0 + t.tl
+#pragma unroll
+  for (int d = 0; d < NU; ++d) ul[d] = 0.0f;
+  float uf[2] = {0.0f, 0.0f};   // finger velocity targets of the current step
 
   const int n_iter = T * ns;
 #pragma unroll 1
@@ -346,45 +353,92 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     // Re-align the warps of the CTA once per sub-step: they then walk the same stretch of this (large) loop body at
     // about the same time and share its instruction-cache lines instead of evicting each other's.
     if (c.align) __syncthreads();
-    if (s == 0 && !last) {
-      // ---- perturbed action of this step (mppi.py:392-416)
-      if (c.noise_mode == M3P2I_NOISE_PHILOX && !c.open_loop) {
-        // the three Philox blocks (dims 0-3, 4-7, 8) are drawn by lanes 0..2 of the team and broadcast
-        float z[4];
-        normal4(c.seed_lo, c.seed_hi, (uint32_t)kg, (uint32_t)step, (uint32_t)min(t.tl, 2), z);
-        float zz[NU];
+    const int lb_ = it & (TM - 1);   // position of this iteration in its block
+    if (lb_ == 0) {
+      // ---- perturbed action (mppi.py:392-416) of the step of the own iteration
+      const int itl = it + t.tl;
+      const int stepl = min(itl / ns, T - 1);
+      const bool mine_live = itl < n_iter;
+      if (mine_live) {
+        sample_action<NU>(c, b, kg, k, stepl, ul);
+        if (valid && itl == stepl * ns) {
 #pragma unroll
-        for (int d = 0; d < NU; ++d) zz[d] = __shfl_sync(kFull, z[d & 3], t.team_base + (d >> 2));
-        perturb_action<NU>(c, b, kg, step, zz, u);
-      } else {
-        sample_action<NU>(c, b, kg, k, step, u);
+          for (int d = 0; d < NU; ++d) b.actions[(size_t)(stepl * NU + d) * K + k] = ul[d];
+        }
       }
-      imp_table = mk(0, 0, 0); imp_shelf = mk(0, 0, 0); imp_cubeb = mk(0, 0, 0); pen = mk(0, 0, 0);
+      float ssn[7], scs[7], sqd[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) { ssn[i] = 0.0f; scs[i] = 1.0f; sqd[i] = 0.0f; }
+#pragma unroll 1
+      for (int l = 0; l < TM; ++l) {
+        const int iti = it + l;
+        if (iti > n_iter) break;
+        const bool lasti = iti == n_iter;
+        const int src = t.team_base + l;
+        // own joint's velocity target from the lane that drew this iteration's action
+        float uj = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) { const float v = __shfl_sync(kFull, ul[i], src); if (jo == i) uj = v; }
+        if (!lasti) {
+          // 1. joint drive of the own joint
+          const float m = P.arm_inertia;
+          float vs = (m * vo + h * D * uj) / (m + h * D);
+          const float f = D * (uj - vs);
+          if (f > ef_o) vs = vo + h * ef_o / m;
+          else if (f < -ef_o) vs = vo - h * ef_o / m;
+          vs = clampf(vs, -vl_o, vl_o);
+          if (qo <= lo_o && vs < 0.0f) vs = 0.0f;
+          if (qo >= up_o && vs > 0.0f) vs = 0.0f;
+          vo = vs;
+        }
+        float sno, cso;
+        sincosf(qo, &sno, &cso);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          const float a_ = __shfl_sync(kFull, sno, t.team_base + i), b_ = __shfl_sync(kFull, cso, t.team_base + i);
+          const float c_ = __shfl_sync(kFull, vo, t.team_base + i);
+          if (t.tl == l) { ssn[i] = a_; scs[i] = b_; sqd[i] = c_; }
+        }
+        if (!lasti) {
+          // 4. position of the own joint
+          float qn = qo + h * vo;
+          if (qn < lo_o) { qn = lo_o; vo = 0.0f; }
+          if (qn > up_o) { qn = up_o; vo = 0.0f; }
+          qo = qn;
+          // state row of a finished step: (q1, qd1) from lane 0, (q2, qd2) from lane 1 (reactive_tamp.py:66-69)
+          const int stepi = iti / ns;
+          if (valid && t.tl < 2 && iti - stepi * ns == ns - 1)
+            reinterpret_cast<float2*>(b.states + (size_t)stepi * K + k)[t.tl] = make_float2(qo, vo);
+        }
+      }
+      fk_from_sincos(P, ssn, scs, sqd, Hl);
+    }
+    // ---- hand pose of this iteration, from the lane that ran its forward kinematics
+    Hand H;
+    {
+      const int src = t.team_base + lb_;
+      H.p = shfl3(Hl.p, src); H.v = shfl3(Hl.v, src); H.w = shfl3(Hl.w, src);
+      H.R.cx = shfl3(Hl.R.cx, src); H.R.cy = shfl3(Hl.R.cy, src); H.R.cz = shfl3(Hl.R.cz, src);
+      if (s == 0 && !last) {
+        uf[0] = __shfl_sync(kFull, ul[7], src); uf[1] = __shfl_sync(kFull, ul[8], src);
+        imp_table = mk(0, 0, 0); imp_shelf = mk(0, 0, 0); imp_cubeb = mk(0, 0, 0); pen = mk(0, 0, 0);
+      }
     }
     if (!last) {
-      // ---- 1. joint drives: lane j of the team integrates joint j (an 8-lane team takes a second round for the
-      // ninth joint), the nine results are broadcast
-#pragma unroll
-      for (int j0 = 0; j0 < 9; j0 += TM) {
-        const int j = min(j0 + t.tl, 8);
-        float qj = e.q[j0], vj = e.qd[j0], uj = u[j0];
-#pragma unroll
-        for (int i = j0 + 1; i < 9; ++i) { if (j == i) { qj = e.q[i]; vj = e.qd[i]; uj = u[i]; } }
-        const float m = j < 7 ? P.arm_inertia : P.finger_mass;
-        float vs = (m * vj + h * D * uj) / (m + h * D);
-        const float f = D * (uj - vs);
-        if (f > P.effort[j]) vs = vj + h * P.effort[j] / m;
-        else if (f < -P.effort[j]) vs = vj - h * P.effort[j] / m;
-        vs = clampf(vs, -P.qd_limit[j], P.qd_limit[j]);
-        if (qj <= P.q_lower[j] && vs < 0.0f) vs = 0.0f;
-        if (qj >= P.q_upper[j] && vs > 0.0f) vs = 0.0f;
-#pragma unroll
-        for (int i = j0; i < 9 && i < j0 + TM; ++i) e.qd[i] = __shfl_sync(kFull, vs, t.team_base + i - j0);
-      }
+      // ---- 1. finger drives: lanes with an even / odd index integrate the left / right finger
+      const int jf = t.tl & 1;
+      const float qj = jf ? e.q[8] : e.q[7], vj = jf ? e.qd[8] : e.qd[7], uj = jf ? uf[1] : uf[0];
+      const float m = P.finger_mass;
+      float vs = (m * vj + h * D * uj) / (m + h * D);
+      const float f = D * (uj - vs);
+      if (f > P.effort[7 + jf]) vs = vj + h * P.effort[7 + jf] / m;
+      else if (f < -P.effort[7 + jf]) vs = vj - h * P.effort[7 + jf] / m;
+      vs = clampf(vs, -P.qd_limit[7 + jf], P.qd_limit[7 + jf]);
+      if (qj <= P.q_lower[7 + jf] && vs < 0.0f) vs = 0.0f;
+      if (qj >= P.q_upper[7 + jf] && vs > 0.0f) vs = 0.0f;
+      e.qd[7] = __shfl_sync(kFull, vs, t.team_base);
+      e.qd[8] = __shfl_sync(kFull, vs, t.team_base + 1);
     }
-    // ---- forward kinematics at the current joint positions (the only FK site)
-    Hand H;
-    team_fk(P, e.q, e.qd, t, H);
 
     if (s == 0 && step > 0) {
       // ---- cost of the step that just ended (same joint positions as this FK; the drives only changed velocities)
@@ -631,7 +685,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     }
     // ---- 4. positions
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {
+    for (int j = 7; j < 9; ++j) {   // the arm joints were integrated by the run-ahead
       float qn = e.q[j] + h * e.qd[j];
       if (qn < P.q_lower[j]) { qn = P.q_lower[j]; e.qd[j] = 0.0f; }
       if (qn > P.q_upper[j]) { qn = P.q_upper[j]; e.qd[j] = 0.0f; }
@@ -663,20 +717,20 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       e.f_table = inv_dt * itab + inv_ns * pen_table;
       e.f_shelf = inv_dt * ishf + inv_ns * pen_shelf;
       e.f_cubeb = inv_dt * icb;
-      if (writer) {
-#pragma unroll
-        for (int d = 0; d < NU; ++d) b.actions[(size_t)(step * NU + d) * K + k] = u[d];
-        b.states[(size_t)step * K + k] = e.state_row();
-      }
     }
   }
   if (producer) return;
   if (writer) { b.cost_sum[k] = run; publish_J(b, c, k, J); }
-  if (c.store_env && valid) {
-    e.store(b.env, K, k, t);
-    if (writer) {
+  if (c.store_env) {
+    // arm joints back from their owner lanes (warp-uniform branch: every team of the launch stores or none does)
 #pragma unroll
-      for (int d = 0; d < NU; ++d) b.vel_target[(size_t)d * K + k] = u[d];
+    for (int i = 0; i < 7; ++i) { e.q[i] = __shfl_sync(kFull, qo, t.team_base + i); e.qd[i] = __shfl_sync(kFull, vo, t.team_base + i); }
+    if (valid) {
+      e.store(b.env, K, k, t);
+      if (t.tl == ((n_iter - 1) & (TM - 1))) {   // the lane that drew the action of the last step
+#pragma unroll
+        for (int d = 0; d < NU; ++d) b.vel_target[(size_t)d * K + k] = ul[d];
+      }
     }
   }
 }

@@ -152,8 +152,9 @@ def test_peer_memory_exchange_matches_unsharded(task, mm, nshard):
     full.close()
 
 
-def test_peer_exchange_reports_a_missing_rank():
+def test_peer_exchange_reports_a_missing_rank(monkeypatch):
     """A rank that never delivers must not hang the GPU: the waits are bounded and the fetch fails loudly."""
+    monkeypatch.setenv("M3P2I_PEER_TIMEOUT_MS", "300")
     K, T = 256, 12
     shards = [_c4(K, T, "pick", False, K_local=K // 2, offset=r * (K // 2))[1] for r in range(2)]
     desc = [s.peer_export() for s in shards]
