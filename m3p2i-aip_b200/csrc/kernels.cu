@@ -72,12 +72,14 @@ DEV void sample_action(const RolloutCfg& c, const RolloutBufs& b, int kg, int kl
   } else {
     const int ts = c.preshifted ? t : min(t + 1, c.T - 1);
     const float* mean = b.seq + (c.multi_modal ? (kg < half ? SEQ_MEAN1 : SEQ_MEAN2) : SEQ_MEAN) * TN + ts * NU;
-    float z[4];
+    float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int d = 0; d < NU; ++d) {
       float delta;
       if (c.noise_mode == M3P2I_NOISE_PHILOX) {
-        if ((d & 3) == 0) normal4(c.seed_lo, c.seed_hi, (uint32_t)kg, (uint32_t)t, (uint32_t)(d >> 2), z);
+        // the block that only feeds dim 8 is not drawn when the gripper command overrides the finger targets below
+        const bool unused = NU == 9 && d == 8 && (c.gripper == M3P2I_GRIPPER_OPEN || c.gripper == M3P2I_GRIPPER_CLOSE);
+        if ((d & 3) == 0 && !unused) normal4(c.seed_lo, c.seed_hi, (uint32_t)kg, (uint32_t)t, (uint32_t)(d >> 2), z);
         delta = z[d & 3];
       } else if (kl >= 0) {
         delta = b.noise ? b.noise[(size_t)(t * NU + d) * K + kl] : 0.0f;
