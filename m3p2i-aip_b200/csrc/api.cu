@@ -75,6 +75,10 @@ struct DevBuf {
     p = nullptr; n = 0;
     cudaError_t e = cudaMalloc(&p, sizeof(T) * std::max<size_t>(count, 1));
     if (e == cudaSuccess) { n = count; e = cudaMemset(p, 0, sizeof(T) * std::max<size_t>(count, 1)); }
+    // The memset runs on the legacy default stream and may still be pending when this returns; the handles work on
+    // non-blocking streams, which do not wait for it. Without this sync a kernel or copy enqueued right after an
+    // allocation could be overwritten by the late memset (seen as a rare run-to-run difference of closed loops).
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
@@ -620,6 +624,7 @@ int m3p2i_create(const M3P2IConfig* cfg, int device, m3p2i_handle* out) {
     memset(&s, 0, sizeof(s));
     s.beta = 1.0;
     e = cudaMemcpy(h->stats.p, &s, sizeof(s), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);   // pageable H2D may still be in flight
   }
   if (e != cudaSuccess) {
     std::string msg = std::string("m3p2i_create: ") + cudaGetErrorString(e);

@@ -445,6 +445,7 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
     // Positions are fixed during a sub-step, so which cube corners touch which fixed box is decided once (pass 0)
     // and remembered as one bit per (fixed box, corner); later passes revisit only those corners.
     unsigned long long hit[2] = {0ull, 0ull};
+    unsigned lnear = 0u;
     for (int p = 0; p < passes; ++p) {
 #pragma unroll
       for (int i = 0; i < 2; ++i)
@@ -476,15 +477,26 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
           if (i == 1) imp_cubeb = imp_cubeb - accS;
         }
       box_vs_box3<true>(C[0], cbox[0], C[1], cbox[1], 0.5f * (P.cube_mu[0] + P.cube_mu[1]), h, P, imp_cubeb);
-      // the finger - cube - finger chain of a grasp settles only after a few sweeps over its own contacts
-      for (int sw = 0; sw < P.link_sweeps; ++sw)
+      // the finger - cube - finger chain of a grasp settles only after a few sweeps over its own contacts; which
+      // link / cube pairs are close is decided once per sub-step (bit 2 f + i), most rollouts have none
+      if (p == 0) {
+        lnear = 0u;
+#pragma unroll
+        for (int f = 0; f < 3; ++f)
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (boxes_near(lbox[f], cbox[i], P.contact_margin)) lnear |= 1u << (2 * f + i);
+      }
+      for (int sw = 0; sw < P.link_sweeps && lnear; ++sw)
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
         V3 sink = mk(0, 0, 0);
-        link_vs_cube(L[f].v, L[f].w, L[f].x, L[f].axis, L[f].slide, L[f].ims, lbox[f], C[0].v, C[0].w, C[0].im, C[0].ii,
-                     C[0].x, cbox[0], 0.5f * (P.robot_mu + P.cube_mu[0]), h, P, sink);
-        link_vs_cube(L[f].v, L[f].w, L[f].x, L[f].axis, L[f].slide, L[f].ims, lbox[f], C[1].v, C[1].w, C[1].im, C[1].ii,
-                     C[1].x, cbox[1], 0.5f * (P.robot_mu + P.cube_mu[1]), h, P, imp_cubeb);
+        if ((lnear >> (2 * f)) & 1u)
+          link_vs_cube(L[f].v, L[f].w, L[f].x, L[f].axis, L[f].slide, L[f].ims, lbox[f], C[0].v, C[0].w, C[0].im, C[0].ii,
+                       C[0].x, cbox[0], 0.5f * (P.robot_mu + P.cube_mu[0]), h, P, sink);
+        if ((lnear >> (2 * f + 1)) & 1u)
+          link_vs_cube(L[f].v, L[f].w, L[f].x, L[f].axis, L[f].slide, L[f].ims, lbox[f], C[1].v, C[1].w, C[1].im, C[1].ii,
+                       C[1].x, cbox[1], 0.5f * (P.robot_mu + P.cube_mu[1]), h, P, imp_cubeb);
       }
     }
 #pragma unroll
