@@ -10,18 +10,20 @@
 // so a team is 16 / CPL lanes and a warp carries 2 * CPL samples. CPL = 1 has the shortest per-sample chain (best
 // while the GPU is far from full), CPL = 2 halves the number of warp-instructions per sample because the serial
 // solves, the forward kinematics and the cost are replicated over 8 instead of 16 lanes.
-// Joint state, forward kinematics and the link boxes are replicated in all lanes of a team (drives, sin/cos and the
-// Philox blocks are computed by one lane each and broadcast). Contact detection runs on all corners at once; the
-// solves are broadcast (warp shuffles) and applied in exactly the pair / corner order of the thread-per-sample code
-// (panda_env.cuh), so both produce the same trajectory up to fp32 rounding of reordered sums.
+// The arm runs ahead of the contacts: no contact acts on the seven velocity-tracked arm joints, so once per block of
+// 16 / CPL iterations lane j advances arm joint j through the whole block and lane l runs the forward kinematics of
+// iteration l of the block; an iteration then fetches its hand pose with shuffles (team_rollout). Finger joints, link
+// boxes and the cost are replicated in all lanes of a team. Contact detection and every geometry-only contact term
+// run on all corners at once; the velocity part of the solves is broadcast (warp shuffles) and applied in exactly the
+// pair / corner order of the thread-per-sample code (panda_env.cuh), so both produce the same trajectory up to fp32
+// rounding of reordered sums.
 // All branches that contain shuffles are warp-uniform (decided by __ballot_sync / __any_sync).
 //
 // Code size is a first-order concern here: with ~14 resident warps per SM at different program counters the kernel
 // is instruction-fetch bound as soon as its loop body outgrows the instruction cache (ncu: 75 % `no_inst` stalls with
-// the unrolled version in contact-rich states). Hence ONE copy of everything: one forward-kinematics site per
-// sub-step (the cost of step t is evaluated from the FK of the first sub-step of step t+1 — same joint positions),
-// link / cube pairs, the two detection directions and the corner slots as rolled loops, one inlined copy of each
-// contact solve.
+// the unrolled version in contact-rich states). Hence ONE copy of everything: one forward-kinematics site (the cost
+// of step t is evaluated from the hand pose of the first sub-step of step t+1 — same joint positions), link / cube
+// pairs, the two detection directions and the corner slots as rolled loops, one inlined copy of each contact solve.
 #pragma once
 #include "panda_env.cuh"
 
@@ -114,7 +116,6 @@ struct TeamEnv {
     s[f * stride] = f_shelf.x; s[(f + 1) * stride] = f_shelf.y; s[(f + 2) * stride] = f_shelf.z; f += 3;
     s[f * stride] = f_cubeb.x; s[(f + 1) * stride] = f_cubeb.y; s[(f + 2) * stride] = f_cubeb.z;
   }
-  DEV float4 state_row() const { return make_float4(q[0], qd[0], q[1], qd[1]); }
 };
 
 // The generic two-body solve is only reached when the two cubes touch each other; one out-of-line copy.
