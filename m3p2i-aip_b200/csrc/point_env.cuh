@@ -98,6 +98,20 @@ DEV void solve_contact2(Dyn2& A, Dyn2& B, float nx, float ny, float depth, float
   ix = jn * nx + jt * tx; iy = jn * ny + jt * ty;
 }
 
+// the broad-phase tests of disc_vs_box / box_vs_box as predicates (same expressions)
+DEV bool disc_near(float px, float py, float reach, const OBox2& bx) {
+  const float ox = px - bx.cx, oy = py - bx.cy;
+  const float dx = bx.c * ox + bx.s * oy, dy = -bx.s * ox + bx.c * oy;
+  return !(fabsf(dx) - bx.hx > reach || fabsf(dy) - bx.hy > reach);
+}
+DEV bool box_near(const OBox2& ba, const OBox2& bb, float margin) {
+  const float ox = ba.cx - bb.cx, oy = ba.cy - bb.cy;
+  const float dx = bb.c * ox + bb.s * oy, dy = -bb.s * ox + bb.c * oy;
+  const float reach = sqrtf(ba.hx * ba.hx + ba.hy * ba.hy) + margin;
+  const float ex = fmaxf(fabsf(dx) - bb.hx, 0.0f), ey = fmaxf(fabsf(dy) - bb.hy, 0.0f);
+  return !(ex * ex + ey * ey > reach * reach);
+}
+
 // robot disc (A) against an oriented box (B); accB accumulates the impulse received by B
 DEV void disc_vs_box(Dyn2& A, float r, Dyn2& B, const OBox2& bx, float mu, float h, const PointParams& P, float& accBx,
                      float& accBy) {
@@ -207,18 +221,31 @@ DEV void point_step(PointEnv& e, const PointParams& P, const float* u, float dt,
     Dyn2 Bx = {e.box.vx, e.box.vy, e.box.w, 1.0f / P.box_mass, 1.0f / P.box_inertia, e.box.x, e.box.y};
     Dyn2 Dy = {e.dyn.vx, e.dyn.vy, e.dyn.w, 1.0f / P.dyn_mass, 1.0f / P.dyn_inertia, e.dyn.x, e.dyn.y};
     const OBox2 bbox = obox_of(e.box, P.box_hx, P.box_hy), dbox = obox_of(e.dyn, P.dyn_hx, P.dyn_hy);
+    // Positions are fixed during a sub-step, so which fixed boxes can touch the robot / the block / the obstacle is
+    // decided once (the broad-phase tests of disc_vs_box and box_vs_box, one bit per fixed box) and every pass visits
+    // only those: same contacts, same order, same arithmetic.
+    unsigned near_r = 0u, near_b = 0u, near_d = 0u;
+    for (int i = 0; i < P.n_static; ++i) {
+      const OBox2 sb = obox_of(P.st[i]);
+      if (disc_near(e.px, e.py, P.robot_radius + P.contact_margin, sb)) near_r |= 1u << i;
+      if (box_near(bbox, sb, P.contact_margin)) near_b |= 1u << i;
+      if (box_near(dbox, sb, P.contact_margin)) near_d |= 1u << i;
+    }
     for (int p = 0; p < passes; ++p) {
-      for (int i = 0; i < P.n_static; ++i) {
+      for (unsigned m_ = near_r; m_; m_ &= m_ - 1u) {
+        const int i = __ffs(m_) - 1;
         Dyn2 S = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, P.st[i].cx, P.st[i].cy};
         disc_vs_box(R, P.robot_radius, S, obox_of(P.st[i]), 0.5f * (P.robot_mu + P.st[i].mu), h, P, sink_x, sink_y);
       }
       disc_vs_box(R, P.robot_radius, Bx, bbox, 0.5f * (P.robot_mu + P.box_mu), h, P, sink_x, sink_y);
       disc_vs_box(R, P.robot_radius, Dy, dbox, 0.5f * (P.robot_mu + P.dyn_mu), h, P, imp_dx, imp_dy);
-      for (int i = 0; i < P.n_static; ++i) {
+      for (unsigned m_ = near_b; m_; m_ &= m_ - 1u) {
+        const int i = __ffs(m_) - 1;
         Dyn2 S = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, P.st[i].cx, P.st[i].cy};
         box_vs_box(Bx, bbox, S, obox_of(P.st[i]), 0.5f * (P.box_mu + P.st[i].mu), h, P, sink_x, sink_y, sink_x, sink_y);
       }
-      for (int i = 0; i < P.n_static; ++i) {
+      for (unsigned m_ = near_d; m_; m_ &= m_ - 1u) {
+        const int i = __ffs(m_) - 1;
         Dyn2 S = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, P.st[i].cx, P.st[i].cy};
         box_vs_box(Dy, dbox, S, obox_of(P.st[i]), 0.5f * (P.dyn_mu + P.st[i].mu), h, P, imp_dx, imp_dy, sink_x, sink_y);
       }
