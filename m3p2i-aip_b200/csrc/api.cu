@@ -382,6 +382,7 @@ UpdateBufs make_ubufs(const H* h) {
   b.cost_sum = h->cost_sum.p; b.partials = h->partials.p; b.seq = h->seq.p; b.filt = h->have_filt ? h->filt.p : nullptr;
   b.cost_total = h->cost_total.p; b.result = h->result.p; b.info = h->info.p;
   b.done_counter = h->ref_flags.p + 2;
+  b.stats_scratch = h->ref_flags.p + 8;
   memset(&b.peer, 0, sizeof(b.peer));
   return b;
 }
@@ -615,8 +616,9 @@ int m3p2i_create(const M3P2IConfig* cfg, int device, m3p2i_handle* out) {
   if (e == cudaSuccess) e = h->cost_total.alloc(K);
   if (e == cudaSuccess) e = h->result.alloc(2 * TN);
   if (e == cudaSuccess) e = h->refs.alloc(T);
-  if (e == cudaSuccess) e = h->ref_flags.alloc(8);   // [0,1] producer progress, [2] fused-update CTA counter,
-                                                      // [3] peer-push ticket, [4] peer-wait error
+  if (e == cudaSuccess) e = h->ref_flags.alloc(16);  // [0,1] producer progress, [2] fused-update CTA counter,
+                                                      // [3] peer-push ticket, [4] peer-wait error,
+                                                      // [8] k_stats CTA counter, [9..11] beta iterations per set
   if (e == cudaSuccess) e = h->stats.alloc(1);
   if (e == cudaSuccess) e = h->info.alloc(1);
   if (e == cudaSuccess) {

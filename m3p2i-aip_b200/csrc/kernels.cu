@@ -378,21 +378,29 @@ DEV void block_argmin(float v, int i, float* shv, int* shi, float& vmin, int& im
 }
 
 // ------------------------------------------------------------------ softmin statistics
+// +1: eta above the band of mppi.py:446-454 (beta shrinks), -1: below it (beta grows), 0: inside
+DEV int eta_adapt(float eta) { return eta > 20.0f ? 1 : (eta < 10.0f ? -1 : 0); }
 // _exp_util (mppi.py:430-456) / _multi_modal_exp_util + update_infinite_beta (m3p2i.py:24-64): min-shift, exp,
 // normaliser eta, on-the-fly beta search, weights. One CTA; the beta search loops on the device (no host sync).
 __global__ void __launch_bounds__(kStatsBlock) k_stats(const UpdateCfg u, const UpdateBufs b) {
   __shared__ float shv[32];
   __shared__ int shi[32];
+  __shared__ int is_last;
   const int Kg = u.Kg, half = Kg / 2;
   const float* J = b.J_global;
   // sharded over peer memory: J_global is the local mailbox; every rank's slice has landed once its flag is up
   if (b.peer.n) wait_flags(b.peer.jflag_local, b.peer.n, b.peer.epoch, b.peer.timeout_ms, b.peer.error);
   Stats* S = b.stats;
-  const int nsets = u.multi_modal ? 3 : 1;
+  // multi-modal: the three weight sets (all / first half / second half) are independent searches: one CTA each
+  const int s = blockIdx.x;
   int iters = 0;
-  for (int i = threadIdx.x; i < 3 * Kg; i += kStatsBlock) b.weights[i] = 0.0f;
+  if (u.multi_modal) {
+    for (int i = threadIdx.x; i < Kg; i += kStatsBlock) b.weights[(size_t)s * Kg + i] = 0.0f;
+  } else {
+    for (int i = threadIdx.x; i < 3 * Kg; i += kStatsBlock) b.weights[i] = 0.0f;
+  }
   __syncthreads();
-  for (int s = 0; s < nsets; ++s) {
+  {
     const int lo = s == 2 ? half : 0, n = s == 0 ? Kg : (s == 1 ? half : Kg - half);
     float v = INFINITY;
     int vi = 0x7fffffff;
@@ -424,30 +432,46 @@ __global__ void __launch_bounds__(kStatsBlock) k_stats(const UpdateCfg u, const 
       S->scale[s] = scale; S->inv_eta[s] = inv; S->eta[s] = eta; S->beta_used[s] = (float)beta; S->jmin[s] = jmin;
       S->best_idx[s] = lo + imin;
     }
-    __syncthreads();
   }
-  if (u.multi_modal) {  // get_pull_preference (m3p2i.py:16-22)
-    float a = 0.0f, c = 0.0f;
-    for (int i = threadIdx.x; i < half; i += kStatsBlock) a += b.weights[i];
-    for (int i = half + threadIdx.x; i < Kg; i += kStatsBlock) c += b.weights[i];
-    a = block_sum<kStatsBlock>(a, shv);
-    c = block_sum<kStatsBlock>(c, shv);
-    if (threadIdx.x == 0) { S->weight_push = a; S->weight_pull = c; }
-  }
-  if (threadIdx.x == 0) {
-    S->beta_iters = iters;
-    if (!u.multi_modal) {
+  if (!u.multi_modal) {
+    if (threadIdx.x == 0) {
+      S->beta_iters = 0;
       S->weight_push = 0.0f; S->weight_pull = 0.0f;
       if (u.env_type == M3P2I_ENV_PANDA) {  // beta adapts across calls (mppi.py:446-454)
-        if (S->eta[0] > 20.0f) S->beta = S->beta * 0.9;
-        else if (S->eta[0] < 10.0f) S->beta = S->beta * 1.2;
+        if (eta_adapt(S->eta[0]) > 0) S->beta = S->beta * 0.9;
+        else if (eta_adapt(S->eta[0]) < 0) S->beta = S->beta * 1.2;
       }
     }
+    return;
+  }
+  // the CTA that finishes last adds up the iterations and evaluates get_pull_preference (m3p2i.py:16-22) on the
+  // weights of the full set (written by CTA 0)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    b.stats_scratch[1 + s] = (unsigned)iters;
+    __threadfence();
+    const unsigned done = atomicAdd(b.stats_scratch, 1u);
+    is_last = done == gridDim.x - 1;
+    if (is_last) *b.stats_scratch = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float a = 0.0f, c = 0.0f;
+  for (int i = threadIdx.x; i < half; i += kStatsBlock) a += __ldcg(b.weights + i);
+  for (int i = half + threadIdx.x; i < Kg; i += kStatsBlock) c += __ldcg(b.weights + i);
+  a = block_sum<kStatsBlock>(a, shv);
+  c = block_sum<kStatsBlock>(c, shv);
+  if (threadIdx.x == 0) {
+    S->weight_push = a; S->weight_pull = c;
+    const volatile unsigned* it = b.stats_scratch + 1;
+    S->beta_iters = (int)(it[0] + it[1] + it[2]);
   }
 }
 
 void launch_stats(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches) {
-  k_stats<<<1, kStatsBlock, 0, st>>>(u, b);
+  k_stats<<<u.multi_modal ? 3 : 1, kStatsBlock, 0, st>>>(u, b);
   ++*launches;
 }
 

@@ -36,6 +36,7 @@ struct UpdateBufs {
   float* result;           // [T*nu] filtered action, followed by [T*nu] unfiltered mean
   M3P2ICommandInfo* info;  // device copy
   unsigned* done_counter;  // CTA completion counter of the fused wsum + finish launch
+  unsigned* stats_scratch; // [0] CTA completion counter of the multi-modal k_stats, [1..3] beta iterations per set
   PeerReduce peer;
 };
 
