@@ -13,10 +13,13 @@
  *   cubes   : cubeA, cubeB are 3-D rigid boxes (isotropic inertia) under gravity. Contacts: box corners
  *             against the signed distance field of the other box (cube-static, cube-cube, finger/hand-cube),
  *             velocity-level Gauss-Seidel impulses with Coulomb friction, speculative margin and Baumgarte
- *             feedback, `solver_passes` sweeps per substep in a fixed pair order. Semi-implicit Euler.
+ *             feedback, `solver_passes` sweeps per substep in a fixed pair order, each with `link_sweeps` (4)
+ *             sweeps over the finger/hand-cube contacts (a squeezed cube settles inside the sub-step).
+ *             Semi-implicit Euler.
  *   links vs statics: the kinematic hand/finger boxes do not stop at the table / shelf; their penetration is
  *             reported as a penalty contact force (k * depth + Coulomb friction) on the static body, which is
- *             what the collision cost reads (cost_functions.py:158-169).
+ *             what the collision cost reads (cost_functions.py:158-169). The cubes' own contacts with the table /
+ *             shelf stand enter that report only when `report_cube_contacts` is set.
  * FK restates franka_panda.urdf:27-242 (URDF fixed-axis rpy, joint axes +z, fingers +y / -y).
  * Costs restate cost_functions.py:91-169 and skill_utils.py:140-180,224-289.
  */
