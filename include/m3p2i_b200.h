@@ -71,6 +71,10 @@ extern "C" {
 /* noise modes */
 #define M3P2I_NOISE_TABLE 0   /* caller-supplied delta[K,T,nu] (reference semantics: sampled once, reused) */
 #define M3P2I_NOISE_PHILOX 1  /* Philox4x32-10 counter RNG evaluated inside the rollout kernel */
+#define M3P2I_NOISE_PHILOX_SPLINE 2 /* the same generator drawing max(T/4, 2) + 2 control points per (sample, dimension),
+                                       blended over the horizon by a uniform quadratic B-spline rescaled to unit variance:
+                                       smooth in time like the reference's Halton splines (mppi_utils.py:80-104,
+                                       skill_utils.py:9-22), no table */
 
 /* error codes */
 #define M3P2I_OK 0

@@ -770,7 +770,7 @@ int m3p2i_get_noise(m3p2i_handle h, float* out) {
   const size_t K = h->cfg.num_samples, TN = (size_t)h->cfg.horizon * h->cfg.nu;
   CK(h->scratch.alloc(2 * K * TN));
   const float* src;
-  if (h->cfg.noise_mode == M3P2I_NOISE_PHILOX) {
+  if (h->cfg.noise_mode != M3P2I_NOISE_TABLE) {
     RolloutCfg c = make_rcfg(h);
     launch_noise_dump(c, h->scratch.p, h->stream);
     src = h->scratch.p;

@@ -181,4 +181,38 @@ DEV void normal4(uint32_t seed_lo, uint32_t seed_hi, uint32_t kg, uint32_t t, ui
   }
 }
 
+
+// M3P2I_NOISE_PHILOX_SPLINE: control points c_0 .. c_{nseg+1} ~ N(0,1) per (sample, dimension) at counters
+// t = 0x40000000 + i; the value at step t is the uniform quadratic B-spline at s = t * nseg / (T - 1), divided by the
+// norm of the three blending weights so that every step keeps unit variance.
+DEV void spline_weights(int t, int T, int& i0, float w[3]) {
+  const int nseg = max(T / 4, 2);
+  const float s = T > 1 ? (float)t * (float)nseg / (float)(T - 1) : 0.0f;
+  i0 = min((int)s, nseg - 1);
+  const float f = s - (float)i0;
+  w[0] = 0.5f * (1.0f - f) * (1.0f - f);
+  w[1] = 0.5f + f - f * f;
+  w[2] = 0.5f * f * f;
+  const float inv = 1.0f / sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  w[0] *= inv; w[1] *= inv; w[2] *= inv;
+}
+
+// four unit normals of (global sample kg, step t, dimension group g) for the counter-based noise modes
+DEV void noise4(int noise_mode, uint32_t seed_lo, uint32_t seed_hi, uint32_t kg, int t, int T, uint32_t g, float z[4]) {
+  if (noise_mode != M3P2I_NOISE_PHILOX_SPLINE) {
+    normal4(seed_lo, seed_hi, kg, (uint32_t)t, g, z);
+    return;
+  }
+  int i0;
+  float w[3], c[4];
+  spline_weights(t, T, i0, w);
+  z[0] = z[1] = z[2] = z[3] = 0.0f;
+#pragma unroll 1
+  for (int j = 0; j < 3; ++j) {
+    normal4(seed_lo, seed_hi, kg, 0x40000000u + (uint32_t)(i0 + j), g, c);
+    const float wj = j == 0 ? w[0] : (j == 1 ? w[1] : w[2]);
+    z[0] += wj * c[0]; z[1] += wj * c[1]; z[2] += wj * c[2]; z[3] += wj * c[3];
+  }
+}
+
 }  // namespace m3

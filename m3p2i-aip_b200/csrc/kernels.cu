@@ -76,10 +76,10 @@ DEV void sample_action(const RolloutCfg& c, const RolloutBufs& b, int kg, int kl
 #pragma unroll
     for (int d = 0; d < NU; ++d) {
       float delta;
-      if (c.noise_mode == M3P2I_NOISE_PHILOX) {
+      if (c.noise_mode != M3P2I_NOISE_TABLE) {
         // the block that only feeds dim 8 is not drawn when the gripper command overrides the finger targets below
         const bool unused = NU == 9 && d == 8 && (c.gripper == M3P2I_GRIPPER_OPEN || c.gripper == M3P2I_GRIPPER_CLOSE);
-        if ((d & 3) == 0 && !unused) normal4(c.seed_lo, c.seed_hi, (uint32_t)kg, (uint32_t)t, (uint32_t)(d >> 2), z);
+        if ((d & 3) == 0 && !unused) noise4(c.noise_mode, c.seed_lo, c.seed_hi, (uint32_t)kg, t, c.T, (uint32_t)(d >> 2), z);
         delta = z[d & 3];
       } else if (kl >= 0) {
         delta = b.noise ? b.noise[(size_t)(t * NU + d) * K + kl] : 0.0f;
@@ -764,7 +764,7 @@ __global__ void k_noise_dump(const __grid_constant__ RolloutCfg c, float* out) {
   for (int t = 0; t < c.T; ++t) {
     float z[4];
     for (int d = 0; d < c.nu; ++d) {
-      if ((d & 3) == 0) normal4(c.seed_lo, c.seed_hi, (uint32_t)kg, (uint32_t)t, (uint32_t)(d >> 2), z);
+      if ((d & 3) == 0) noise4(c.noise_mode, c.seed_lo, c.seed_hi, (uint32_t)kg, t, c.T, (uint32_t)(d >> 2), z);
       out[(size_t)(t * c.nu + d) * c.K + k] = z[d & 3];
     }
   }

@@ -30,7 +30,7 @@ class MPPIConfig(object):
     horizon: int = 12
     nx: int = 4
     mppi_mode: str = 'halton-spline'
-    sampling_method: str = "halton"   # "halton" | "random" | "philox" (in-kernel counter RNG)
+    sampling_method: str = "halton"   # "halton" | "random" | in-kernel counter RNG: "philox" (white), "philox-spline" (smooth)
     noise_sigma: Optional[List[List[float]]] = None
     noise_mu: Optional[List[float]] = None
     device: str = "cuda:0"
@@ -112,7 +112,7 @@ class MPPI():
         self.fused = (isinstance(sim, IsaacGymWrapper) and isinstance(obj, Objective)
                       and getattr(running_cost, "__self__", None) is owner and getattr(m, "fused", True)
                       and sim.num_envs == self.K)
-        noise_mode = A.NOISE_PHILOX if self.sampling_method == "philox" else A.NOISE_TABLE
+        noise_mode = {"philox": A.NOISE_PHILOX, "philox-spline": A.NOISE_PHILOX_SPLINE}.get(self.sampling_method, A.NOISE_TABLE)
         if self.fused:
             self._sim, self._objective = sim, obj
             self.backend = sim.attach_planner(cfg, noise_mode=noise_mode, seed=self.seed_val)
@@ -162,14 +162,14 @@ class MPPI():
         return torch.randn(*shape, self.nu, generator=self._rng) @ L.T
 
     def _ensure_noise(self):
-        if self.sampling_method == "philox" and self._delta is None:
+        if self.sampling_method in ("philox", "philox-spline") and self._delta is None:
             return
         if self.sampling_method == "random" or self._delta is None:
             self.delta = self.get_samples(self.K, base_seed=0)
         if not self._delta_uploaded:
             d = self._delta.detach().cpu().numpy() if torch.is_tensor(self._delta) else np.asarray(self._delta)
             if self.backend.cfg.noise_mode != A.NOISE_TABLE:
-                raise RuntimeError("a delta table was given but the planner was created with sampling_method='philox'")
+                raise RuntimeError("a delta table was given but the planner was created with an in-kernel sampling_method")
             self.backend.set_noise_table(d)
             self._delta_uploaded = True
 

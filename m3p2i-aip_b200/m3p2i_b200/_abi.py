@@ -17,7 +17,7 @@ ENV_IDS = {"point_env": ENV_POINT, "panda_env": ENV_PANDA}
 TASK_IDS = {"navigation": 0, "push": 1, "pull": 2, "push_pull": 3, "reach": 4, "pick": 5, "place": 6}
 GRIPPER_IDS = {None: 0, "none": 0, "open": 1, "close": 2}
 
-NOISE_TABLE, NOISE_PHILOX = 0, 1
+NOISE_TABLE, NOISE_PHILOX, NOISE_PHILOX_SPLINE = 0, 1, 2
 
 BUF_ACTIONS, BUF_STATES, BUF_COST_HORIZON, BUF_COST_DISC, BUF_COST_SUM, BUF_WEIGHTS, BUF_NOISE = range(7)
 

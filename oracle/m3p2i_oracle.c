@@ -84,8 +84,24 @@ static inline float o_noise(const Oracle* o, int k, int t, int d) {
     return o->delta ? o->delta[((size_t)k * c->horizon + t) * c->nu + d] : 0.0f;
   }
   float z[4];
-  o_normal4(c->seed, (uint32_t)(c->sample_offset + k), (uint32_t)t, (uint32_t)(d >> 2), z);
-  return z[d & 3];
+  if (c->noise_mode != M3P2I_NOISE_PHILOX_SPLINE) {
+    o_normal4(c->seed, (uint32_t)(c->sample_offset + k), (uint32_t)t, (uint32_t)(d >> 2), z);
+    return z[d & 3];
+  }
+  /* M3P2I_NOISE_PHILOX_SPLINE (include/m3p2i_b200.h): uniform quadratic B-spline over nseg + 2 control points drawn
+   * at counters 0x40000000 + i, rescaled to unit variance */
+  const int T = c->horizon, nseg = T / 4 > 2 ? T / 4 : 2;
+  const float s = T > 1 ? (float)t * (float)nseg / (float)(T - 1) : 0.0f;
+  int i0 = (int)s < nseg - 1 ? (int)s : nseg - 1;
+  const float f = s - (float)i0;
+  float w[3] = {0.5f * (1.0f - f) * (1.0f - f), 0.5f + f - f * f, 0.5f * f * f};
+  const float inv = 1.0f / sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  float acc = 0.0f;
+  for (int j = 0; j < 3; ++j) {
+    o_normal4(c->seed, (uint32_t)(c->sample_offset + k), 0x40000000u + (uint32_t)(i0 + j), (uint32_t)(d >> 2), z);
+    acc += (w[j] * inv) * z[d & 3];
+  }
+  return acc;
 }
 
 /* ------------------------------------------------------------------ lifecycle */

@@ -225,6 +225,25 @@ def _sample_mismatch(a, b, rtol, atol):
     return bad.reshape(bad.shape[0], -1).any(axis=1).mean()
 
 
+@pytest.mark.parametrize("case", [CASES[1], CASES[4], CASES[5]], ids=["push_c2", "reach", "reach_mm"])
+def test_command_matches_oracle_philox_spline(case):
+    """M3P2I_NOISE_PHILOX_SPLINE: the smooth in-kernel noise (B-spline over Philox control points) against the oracle
+    evaluating the same counters, thread-per-sample (point) and team kernels (panda), two ticks."""
+    O.set_threads(8)
+    cfg, o, n = _setup(case, A.NOISE_PHILOX_SPLINE)
+    assert_close(n.get_noise(), o.get_noise(), 1e-4, 2e-5, f"{case[0]} philox-spline noise")
+    bad = 0.005 if case[2] == "push" else 0.0
+    for i in range(2):
+        a_o, c_o, _ = o.command()
+        a_n, c_n, _ = n.command()
+        assert_close(n.read_buffer(A.BUF_ACTIONS), o.read_buffer(A.BUF_ACTIONS), 1e-4, 1e-4, f"{case[0]}[{i}] actions", bad)
+        assert_close(n.read_buffer(A.BUF_COST_HORIZON), o.read_buffer(A.BUF_COST_HORIZON), RTOL, ATOL,
+                     f"{case[0]}[{i}] cost_horizon", bad)
+        assert_close(a_n, a_o, 1e-3, 1e-3, f"{case[0]}[{i}] action")
+    o.close()
+    n.close()
+
+
 GRASP_Q = [-0.21448, 1.040633, -0.091726, -1.527796, 0.144743, 2.56178, 0.807333, 0.027, 0.027]  # make_golden.grasp_pose
 
 

@@ -56,3 +56,30 @@ def test_oracle_reproduces_reference(name):
         assert np.array_equal(idx[distinct], g[f"top_idx_{i}"][distinct]), f"{name}[{i}] top_idx"
         assert_close(trajs[distinct], g[f"top_trajs_{i}"][distinct], RTOL, ATOL, f"{name}[{i}] top_trajs")
     o.close()
+
+
+def test_philox_spline_noise_is_smooth_and_unit_variance():
+    """M3P2I_NOISE_PHILOX_SPLINE (include/m3p2i_b200.h): N(0,1) control points blended by a uniform quadratic
+    B-spline and rescaled: every step has unit variance, neighbouring steps are strongly correlated (white Philox
+    noise is not), samples and dimensions are independent, and the table is a pure function of (seed, k, t, d)."""
+    from m3p2i_b200 import scene as S
+    K, T = 4096, 32
+    cfg = S.make_cfg("panda_env", "reach", None, K, T)
+    tabs = {}
+    for mode in (A.NOISE_PHILOX, A.NOISE_PHILOX_SPLINE):
+        o = make_backend(O.Oracle, cfg, noise_mode=mode, seed=5)
+        tabs[mode] = np.asarray(o.get_noise()).reshape(K, T, 9)[:-1]     # the last sample is the zero-noise one
+        o.close()
+    z = tabs[A.NOISE_PHILOX_SPLINE]
+    assert np.abs(z.mean(axis=0)).max() < 0.08
+    assert np.abs(z.std(axis=0) - 1.0).max() < 0.06
+    lag1 = (z[:, 1:] * z[:, :-1]).mean(axis=(0, 2))
+    assert lag1.min() > 0.8                                             # smooth in time
+    assert np.abs((tabs[A.NOISE_PHILOX][:, 1:] * tabs[A.NOISE_PHILOX][:, :-1]).mean()) < 0.02   # white
+    assert np.abs((z[:, T // 2, 0] * z[:, T // 2, 1]).mean()) < 0.06    # dimensions independent
+    assert np.abs((z[1:, 3, 0] * z[:-1, 3, 0]).mean()) < 0.06           # samples independent
+    far = (z[:, 0] * z[:, -1]).mean()
+    assert abs(far) < 0.06                                              # both ends of the horizon decorrelate
+    o = make_backend(O.Oracle, cfg, noise_mode=A.NOISE_PHILOX_SPLINE, seed=5)
+    assert np.array_equal(np.asarray(o.get_noise()).reshape(K, T, 9)[:-1], z)
+    o.close()
