@@ -28,7 +28,11 @@
  *   m3p2i_sim_*                    <- the IsaacGymWrapper facade on K persistent envs: step()
  *                                     (isaacgym_wrapper.py:354-360), set_dof_velocity_target_tensor (:196),
  *                                     apply_rigid_body_force_tensors (:202), tensor views (:98-112)
- *   m3p2i_comm_init                <- (nothing: the reference is single-GPU) K sharded over ranks, NCCL
+ *   m3p2i_peer_export / _attach    <- (nothing: the reference is single-GPU) K sharded over ranks; the all-gather
+ *                                     of the discounted costs and the all-reduce of the weighted action sums are
+ *                                     stores into peer HBM over NVLink issued by the rollout / weighted-sum kernels
+ *   m3p2i_comm_init                <- (nothing) the same exchange as two NCCL collectives (fallback)
+ *   m3p2i_phase_*                  <- (nothing) the same three phases host-staged, for any transport
  *
  * Conventions: plain C, caller owns every host array (C-contiguous fp32 / int32), the library owns all
  * device memory. Return 0 on success, negative code on failure; the message is in m3p2i_last_error().
