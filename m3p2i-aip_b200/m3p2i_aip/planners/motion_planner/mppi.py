@@ -68,6 +68,12 @@ class MPPI():
         if self.mppi_mode not in ("halton-spline", "simple"):
             raise ValueError(f"unknown mppi_mode {self.mppi_mode!r}")
         self.sampling_method = getattr(m, "sampling_method", "halton")
+        if self.sampling_method not in ("halton", "random", "philox", "philox-spline"):
+            raise ValueError(f"unknown sampling_method {self.sampling_method!r}")
+        # branches of the reference that no shipped YAML enables and this planner does not implement: say so instead
+        # of silently planning with a fixed covariance (mppi.py:43,508-516)
+        if bool(getattr(m, "update_cov", False)):
+            raise NotImplementedError("mppi.update_cov=True (covariance adaptation, mppi.py:508-516) is not implemented")
         self.K = int(m.num_samples)
         self.half_K = int(self.K / 2)
         self.T = int(m.horizon)

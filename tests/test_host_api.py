@@ -152,3 +152,15 @@ def test_simple_mode_update_and_progress():
         real.set_dof_velocity_target_tensor(action[0].view(1, -1))
         real.step()
     assert float(torch.linalg.norm(real.robot_pos[0] - goal)) < 0.5 * d0
+
+
+def test_unsupported_options_fail_loudly():
+    from m3p2i_b200 import scene as S
+    cfg = S.make_cfg("point_env", "navigation", [1.0, 1.0], 32, 12)
+    cfg.mppi.update_cov = True
+    with pytest.raises(NotImplementedError, match="update_cov"):
+        Tamp(cfg, O.Oracle.for_sim)
+    cfg = S.make_cfg("point_env", "navigation", [1.0, 1.0], 32, 12)
+    cfg.mppi.sampling_method = "sobol"
+    with pytest.raises(ValueError, match="sampling_method"):
+        Tamp(cfg, O.Oracle.for_sim)
