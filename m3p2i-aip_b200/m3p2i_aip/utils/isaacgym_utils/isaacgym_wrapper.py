@@ -29,11 +29,24 @@ class IsaacGymConfig():
     spacing: float = 10
     camera_pos: List[float] = field(default_factory=lambda: [1.5, 6, 8])
     camera_target: List[float] = field(default_factory=lambda: [1.5, 0, 0])
+    # not in the reference: after a fused command() the K envs hold the END states of the rollouts, as in the reference,
+    # and the first access to a tensor view reads all of them back (2.5 MB at K=4096) -- which run_tamp then overwrites
+    # with the real state (reactive_tamp.py:45-48). True skips that read-back: the views keep what was last written.
+    skip_rollout_readback: bool = False
 
 
 _LINKS = {"point_env": {("point_robot", "link_y"): 0},
           "panda_env": {("panda", "panda_leftfinger"): 0, ("panda", "panda_rightfinger"): 1, ("panda", "panda_hand"): 2}}
 _CONTACTS = {"point_env": {"dyn-obs": 0}, "panda_env": {"table": 0, "shelf_stand": 1, "cubeB": 2}}
+
+
+def _rows_equal(a):
+    """True when every env row of a [K, ...] array equals row 0 (the `_dof_state[:] = one_state` broadcast of
+    reactive_tamp.py:45-46): each row against its predecessor on the flat contiguous buffer -- 3x cheaper than comparing
+    with a stride-0 broadcast view, and this check runs on every tick."""
+    flat = np.ascontiguousarray(a).reshape(-1)
+    row = flat.size // a.shape[0]
+    return bool(np.array_equal(flat[row:], flat[:-row]))
 
 
 class IsaacGymWrapper:
@@ -101,8 +114,7 @@ class IsaacGymWrapper:
             return
         b = self._ensure_backend()
         dof, root = self.__dof.numpy(), self.__root.numpy()
-        if self.num_envs == 1 or (np.array_equal(dof, np.broadcast_to(dof[0], dof.shape))
-                                  and np.array_equal(root, np.broadcast_to(root[0], root.shape))):
+        if self.num_envs == 1 or (_rows_equal(dof) and _rows_equal(root)):
             b.set_state(dof[0], root[0])
         else:
             b.set_state(dof[0], root[0])   # fixed actors / floating plate pose
@@ -122,7 +134,10 @@ class IsaacGymWrapper:
 
     def mark_device_advanced(self):
         """The fused command() moved the K envs on the device."""
-        self._host_dirty = True
+        if getattr(self.cfg, "skip_rollout_readback", False):
+            self._push_pending = True   # the device envs no longer match the host mirrors: re-push before the next device op
+        else:
+            self._host_dirty = True
 
     # ------------------------------------------------------------------ tensor views
     @property

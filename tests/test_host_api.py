@@ -164,3 +164,36 @@ def test_unsupported_options_fail_loudly():
     cfg.mppi.sampling_method = "sobol"
     with pytest.raises(ValueError, match="sampling_method"):
         Tamp(cfg, O.Oracle.for_sim)
+
+
+def test_skip_rollout_readback_is_equivalent_for_the_run_tamp_flow():
+    """isaacgym.skip_rollout_readback (not in the reference): the tensor views are not refreshed with the rollouts' end
+    states after a fused command; the run_tamp flow, which overwrites them with the real state first, gives identical
+    actions and never reads the K envs back."""
+    from m3p2i_b200 import scene as S
+    outs, reads = [], []
+    for skip in (False, True):
+        cfg = S.make_cfg("point_env", "push", [-1.0, -1.0], 64, 12)
+        cfg.isaacgym.skip_rollout_readback = skip
+        t = Tamp(cfg, O.Oracle.for_sim)
+        t.motion_planner.delta = torch.from_numpy(np.random.default_rng(0).standard_normal((64, 12, 2)).astype(np.float32))
+        n = {"reads": 0}
+        orig = t.sim.backend.sim_read
+
+        def counted(orig=orig, n=n):
+            n["reads"] += 1
+            return orig()
+        t.sim.backend.sim_read = counted
+        actors = S.default_actors("point_env")
+        dof = torch.from_numpy(S.initial_dof_state(actors)).view(1, -1).clone()
+        dof[0, 0], dof[0, 2] = 0.2, 2.45
+        root = torch.from_numpy(S.initial_root_state(actors)).view(1, -1, 13)
+        acts = []
+        for _ in range(3):
+            a = t.run_tamp(dof, root, "push", torch.tensor([-1.0, -1.0]), False)
+            acts.append(a.clone())
+            dof[0, 0] += 0.01
+        outs.append(torch.stack(acts))
+        reads.append(n["reads"])
+    assert torch.equal(outs[0], outs[1])
+    assert reads[1] == 0 and reads[0] >= 2
