@@ -232,6 +232,8 @@ class NativePlanner:
 
     def peer_attach(self, rank, nranks, descriptors):
         """descriptors: the peer_export() bytes of every rank, indexed by rank. Follow with a host barrier."""
+        if len(descriptors) != nranks or any(len(d) != C.sizeof(A.PeerHandle) for d in descriptors):
+            raise ValueError(f"need {nranks} descriptors of {C.sizeof(A.PeerHandle)} bytes (peer_export() of every rank)")
         arr = (A.PeerHandle * nranks)(*[A.PeerHandle.from_buffer_copy(d) for d in descriptors])
         self._ck(self.fn["m3p2i_peer_attach"](self.h, rank, nranks, arr), "m3p2i_peer_attach")
 
