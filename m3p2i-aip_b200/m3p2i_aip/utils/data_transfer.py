@@ -21,3 +21,12 @@ def numpy_to_bytes(t: np.ndarray) -> bytes:
 
 def bytes_to_numpy(b: bytes):
     return bytes_to_torch(b)
+
+
+def check_server(server_address):
+    """Remove a stale unix-socket file before binding (data_transfer.py:24-29); a missing file is fine."""
+    import os
+    try:
+        os.unlink(server_address)
+    except FileNotFoundError:
+        pass

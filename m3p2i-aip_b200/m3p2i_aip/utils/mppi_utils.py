@@ -61,3 +61,35 @@ def halton_spline_table(K, T, nu, knot_scale=4, degree=2):
         for j in range(nu):
             out[i, :, j] = bspline(knots[i, j], n=T, degree=degree)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Small public helpers of the reference module that user code may import. Inside command() both run in the CUDA
+# kernels (clamping in the rollout kernel, discounting in its cost accumulation); these host versions exist for callers.
+def scale_ctrl(ctrl, action_lows, action_highs, squash_fn="clamp"):
+    """Bound a control sequence (mppi_utils.py:28-44): "clamp" to [lows, highs]; "clamp_rescale" / "tanh" map [-1, 1] onto
+    the range; "identity" returns the input. 1-D input is treated as [1, nu, 1] like the reference does."""
+    import torch
+    if ctrl.dim() == 1:
+        ctrl = ctrl.view(1, -1, 1)
+    if squash_fn == "identity":
+        return ctrl
+    if squash_fn == "clamp":
+        return torch.maximum(torch.minimum(ctrl, action_highs), action_lows)
+    if squash_fn == "clamp_rescale":
+        unit = ctrl.clamp(-1.0, 1.0)
+    elif squash_fn == "tanh":
+        unit = torch.tanh(ctrl)
+    else:
+        raise ValueError(f"unknown squash_fn {squash_fn!r}")
+    mid, half = 0.5 * (action_highs + action_lows), 0.5 * (action_highs - action_lows)
+    return mid.unsqueeze(0) + unit * half.unsqueeze(0)
+
+
+def cost_to_go(cost_seq, gamma_seq):
+    """Discounted cost-to-go of every step (mppi_utils.py:106-113): out[:, t] = sum_{s >= t} gamma^(s - t) * c[:, s]
+    for gamma_seq = gamma^[0..T-1]; column 0 is the discounted trajectory cost the softmin uses."""
+    import torch
+    weighted = gamma_seq * cost_seq
+    tail_sums = torch.flip(torch.cumsum(torch.flip(weighted, dims=[-1]), dim=-1), dims=[-1])
+    return tail_sums / gamma_seq

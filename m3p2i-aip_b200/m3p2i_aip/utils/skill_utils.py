@@ -8,6 +8,8 @@ import time
 
 import torch
 
+from m3p2i_aip.utils.mppi_utils import bspline  # noqa: F401  (the reference defines it here, skill_utils.py:9-22)
+
 
 def time_tracking(t, cfg):
     """Sleep up to the sim dt and report the real-time factor (skill_utils.py:25-33)."""

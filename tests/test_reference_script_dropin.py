@@ -155,3 +155,20 @@ def test_sim_and_reactive_tamp_loop_unchanged(reactive_tamp, monkeypatch, capsys
     robot = created[0].robot_pos[0]
     d0 = float(np.linalg.norm(np.array([1.0, -0.8])))
     assert float(torch.linalg.norm(robot - torch.tensor([1.0, -0.8]))) < 0.5 * d0, robot.tolist()
+
+
+def test_small_host_helpers_match_reference():
+    """scale_ctrl / cost_to_go (public helpers of utils/mppi_utils.py) against the reference's own functions."""
+    sys.modules.setdefault("ghalton", types.ModuleType("ghalton"))
+    spec = importlib.util.spec_from_file_location("ref_mppi_utils", os.path.join(REF, "src", "m3p2i_aip", "utils", "mppi_utils.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from m3p2i_aip.utils import mppi_utils as ours
+    g = torch.Generator().manual_seed(1)
+    c = torch.rand(16, 12, generator=g) * 5
+    gam = 0.95 ** torch.arange(12, dtype=torch.float32)
+    assert torch.allclose(ours.cost_to_go(c.clone(), gam), ref.cost_to_go(c.clone(), gam), atol=1e-5)
+    u = torch.randn(8, 5, 2, generator=g) * 3
+    lo, hi = torch.tensor([-1.0, -2.0]), torch.tensor([1.5, 2.0])
+    for fn in ("clamp", "clamp_rescale", "tanh", "identity"):
+        assert torch.allclose(ours.scale_ctrl(u.clone(), lo, hi, fn), ref.scale_ctrl(u.clone(), lo, hi, fn), atol=1e-6), fn
