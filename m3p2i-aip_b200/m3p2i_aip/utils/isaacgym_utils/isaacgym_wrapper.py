@@ -266,6 +266,17 @@ class IsaacGymWrapper:
     def play_with_cube(self):
         pass  # keyboard interaction of the reference viewer (isaacgym_wrapper.py:421-433): no viewer here
 
+    def visualize_trajs(self, trajs):
+        """The reference draws the planner's top trajectories as lines in its viewer (isaacgym_wrapper.py:374-391,
+        sim.py:54-56). There is no viewer here: the trajectories [n, T, 2 or 3] are kept for the caller to plot."""
+        self.last_trajs = trajs.detach().cpu().clone() if torch.is_tensor(trajs) else np.array(trajs, copy=True)
+
+    def initialize_keyboard_listeners(self):
+        pass  # viewer-only (isaacgym_wrapper.py:393-405)
+
+    def keyboard_control(self):
+        pass  # viewer-only (isaacgym_wrapper.py:407-419)
+
     def step(self):
         self._push()
         self.backend.sim_step()
