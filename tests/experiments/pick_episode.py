@@ -1,9 +1,9 @@
 """Closed-loop reactive pick on the native backend: reach -> pick (-> place), task switching by the thresholds of
 PLANNER_AIF_PANDA (task_planner.py:57-75). Prints the trace; exit code 0 if the cube ends within 5 cm of the goal.
-usage: python tools/pick_episode.py [K] [H] [ticks]"""
+usage: [PICK_BACKEND=oracle] [PICK_SAMPLING=halton|philox|philox-spline] python tests/experiments/pick_episode.py [K] [H] [ticks]"""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [os.path.join(ROOT, "m3p2i-aip_b200"), os.path.join(ROOT, "tests"), ROOT]
 from m3p2i_b200 import scene as S
 from m3p2i_aip.planners.motion_planner import m3p2i

@@ -1,7 +1,7 @@
 """Three physics probes of the Panda integrator on the CPU oracle (K=1 "real world" env through the sim facade):
 resting creep of cubeA over 400 ticks, squeeze-and-lift (finger creep, tangential table load, cube creep, lift), and a
 closed gripper pressed down onto cubeA (does the cube tunnel through the table?).
-    python tools/experiments/solver_probe.py [link_sweeps]
+    python tests/experiments/solver_probe.py [link_sweeps]
 Used at the end of round 1 to evaluate the pass order in fixed_boxes_last.patch (see README.md here)."""
 import os
 import sys
