@@ -176,7 +176,7 @@ typedef struct M3P2IPandaScene {
   float qd_limit[M3P2I_MAX_NU]; /* <limit velocity> */
   float effort[M3P2I_MAX_NU];   /* <limit effort> */
   float drive_damping;   /* 600, isaacgym_wrapper.py:344 */
-  float arm_inertia;     /* reflected inertia used by the implicit velocity drive of the 7 arm joints */
+  float arm_inertia;     /* reflected inertia of an arm joint whose joint_inertia entry is <= 0 */
   float finger_mass;     /* mass of one finger (prismatic DoF) */
   float robot_mu;        /* friction of the panda shapes */
   float finger_half[3];  /* finger collision box (AABB of meshes/collision/finger.obj), centred at finger_center */
@@ -188,6 +188,14 @@ typedef struct M3P2IPandaScene {
   float slop;
   float max_corr_vel;
   float penalty_stiffness; /* kinematic link vs static box: force = k * depth (reported as contact force only) */
+  float joint_inertia[M3P2I_MAX_NU]; /* inertia the velocity drive of arm joint j works against (entries 0..6; <= 0:
+                            arm_inertia). The URDF has no <inertial> blocks, so IsaacGym derives the link masses from
+                            the collision meshes at its default density; tools/panda_inertia.py does the same and
+                            reflects them onto the joint axes at the initial pose */
+  float warm_start;      /* fraction of a contact's accumulated impulse re-applied in the next sub-step of a step() */
+  float sleep_lin;       /* a supported, untouched cube slower than this (m/s; and sleep_ang rad/s) is asleep: it is */
+  float sleep_ang;       /*   neither moved nor solved (PhysX sleeps resting bodies too); sleep_lin <= 0: never */
+  float sleep_gap;       /* a corner counts as supporting when it is within this distance of the fixed box (m) */
   int32_t n_static;
   int32_t n_actors;
   int32_t idx_table;     /* index into statics[] of the bodies named by get_motion_cost (cost_functions.py:161-164) */

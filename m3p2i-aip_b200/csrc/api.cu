@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "params_host.h"
 
 using namespace m3;
 
@@ -133,65 +134,6 @@ typedef M3P2IHandle_ H;
 
 int ndof_of(const H* h) { return h->cfg.env_type == M3P2I_ENV_POINT ? 2 : 9; }
 int nf_of(const H* h) { return h->cfg.env_type == M3P2I_ENV_POINT ? kPointEnvFloats : kPandaEnvFloats; }
-
-Static2 make_static2(const M3P2IBox& b) {
-  const float x = b.quat[0], y = b.quat[1], z = b.quat[2], w = b.quat[3];
-  const float c = 1.0f - 2.0f * (y * y + z * z), s = 2.0f * (w * z + x * y);
-  const float n = sqrtf(c * c + s * s);
-  Static2 r;
-  r.cx = b.pos[0]; r.cy = b.pos[1]; r.hx = b.half[0]; r.hy = b.half[1];
-  r.c = c / n; r.s = s / n; r.mu = b.mu; r.rad = sqrtf(r.hx * r.hx + r.hy * r.hy);
-  return r;
-}
-
-Static3 make_static3(const M3P2IBox& b) {
-  Static3 r;
-  const float x = b.quat[0], y = b.quat[1], z = b.quat[2], w = b.quat[3];
-  memcpy(r.c, b.pos, sizeof(r.c));
-  memcpy(r.half, b.half, sizeof(r.half));
-  r.R[0] = 1.0f - 2.0f * (y * y + z * z); r.R[1] = 2.0f * (x * y - w * z); r.R[2] = 2.0f * (x * z + w * y);
-  r.R[3] = 2.0f * (x * y + w * z); r.R[4] = 1.0f - 2.0f * (x * x + z * z); r.R[5] = 2.0f * (y * z - w * x);
-  r.R[6] = 2.0f * (x * z - w * y); r.R[7] = 2.0f * (y * z + w * x); r.R[8] = 1.0f - 2.0f * (x * x + y * y);
-  r.mu = b.mu;
-  return r;
-}
-
-void build_point_params(H* h) {
-  const M3P2IPointScene& s = h->ps_in;
-  PointParams& p = h->pp;
-  p.robot_radius = s.robot_radius; p.robot_mass = s.robot_mass; p.robot_mu = s.robot_mu;
-  p.drive_damping = s.drive_damping; p.drive_effort = s.drive_effort; p.gravity = s.gravity; p.ground_mu = s.ground_mu;
-  p.contact_margin = s.contact_margin; p.baumgarte = s.baumgarte; p.slop = s.slop; p.max_corr_vel = s.max_corr_vel;
-  p.box_hx = s.box.half[0]; p.box_hy = s.box.half[1]; p.box_mass = s.box.mass; p.box_inertia = s.box.inertia;
-  p.box_mu = s.box.mu; p.box_reff = s.box.r_eff;
-  p.dyn_hx = s.dyn_obs.half[0]; p.dyn_hy = s.dyn_obs.half[1]; p.dyn_mass = s.dyn_obs.mass;
-  p.dyn_inertia = s.dyn_obs.inertia; p.dyn_mu = s.dyn_obs.mu; p.dyn_reff = s.dyn_obs.r_eff;
-  p.n_static = s.n_static;
-  for (int i = 0; i < s.n_static; ++i) p.st[i] = make_static2(s.statics[i]);
-}
-
-void build_panda_params(H* h) {
-  const M3P2IPandaScene& s = h->qs_in;
-  PandaParams& p = h->qp;
-  memcpy(p.base, s.base_pos, sizeof(p.base));
-  p.gravity = s.gravity;
-  memcpy(p.q_lower, s.q_lower, sizeof(p.q_lower)); memcpy(p.q_upper, s.q_upper, sizeof(p.q_upper));
-  memcpy(p.qd_limit, s.qd_limit, sizeof(p.qd_limit)); memcpy(p.effort, s.effort, sizeof(p.effort));
-  p.drive_damping = s.drive_damping; p.arm_inertia = s.arm_inertia; p.finger_mass = s.finger_mass; p.robot_mu = s.robot_mu;
-  memcpy(p.finger_half, s.finger_half, 12); memcpy(p.finger_center, s.finger_center, 12);
-  memcpy(p.hand_half, s.hand_half, 12); memcpy(p.hand_center, s.hand_center, 12);
-  p.contact_margin = s.contact_margin; p.baumgarte = s.baumgarte; p.slop = s.slop; p.max_corr_vel = s.max_corr_vel;
-  p.penalty_stiffness = s.penalty_stiffness;
-  p.link_sweeps = s.link_sweeps > 0 ? s.link_sweeps : 4;
-  p.report_cube = s.report_cube_contacts ? 1 : 0;
-  const M3P2IBody* cb[2] = {&s.cube_a, &s.cube_b};
-  for (int i = 0; i < 2; ++i) {
-    memcpy(p.cube_half[i], cb[i]->half, 12);
-    p.cube_mass[i] = cb[i]->mass; p.cube_inertia[i] = cb[i]->inertia; p.cube_mu[i] = cb[i]->mu;
-  }
-  p.n_static = s.n_static; p.idx_table = s.idx_table; p.idx_shelf = s.idx_shelf;
-  for (int i = 0; i < s.n_static; ++i) p.st[i] = make_static3(s.statics[i]);
-}
 
 // one env in field order from the reference tensors (dof_state, root_state)
 void pack_env(const H* h, const float* dof, const float* root, float* f) {
@@ -676,7 +618,7 @@ int m3p2i_set_scene_point(m3p2i_handle h, const M3P2IPointScene* s) {
     return fail(M3P2I_ERR_ARG, "box / dyn_obs actor rows out of range");
   h->ps_in = *s;
   h->n_actors = s->n_actors;
-  build_point_params(h);
+  build_point_params(h->ps_in, h->pp);
   h->have_scene = true;
   return 0;
 }
@@ -690,7 +632,7 @@ int m3p2i_set_scene_panda(m3p2i_handle h, const M3P2IPandaScene* s) {
     return fail(M3P2I_ERR_ARG, "cube actor rows out of range");
   h->qs_in = *s;
   h->n_actors = s->n_actors;
-  build_panda_params(h);
+  build_panda_params(h->qs_in, h->qp);
   h->have_scene = true;
   return 0;
 }

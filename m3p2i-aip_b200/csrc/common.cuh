@@ -2,11 +2,21 @@
 // Layout of everything in HBM is structure-of-arrays with the sample index fastest, so that a warp's
 // loads and stores of one field are one contiguous 128-byte line.
 #pragma once
+#ifndef M3_EMU
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include "../../include/m3p2i_b200.h"
 
 #define DEV __device__ __forceinline__
+
+// Two constructs that the host build of the device code (tests/emu: the lock-step warp emulator) replaces:
+// an optimisation barrier that pins nine floats as values, and the CTA's dynamic shared memory.
+#ifndef M3_EMU
+#define M3_PIN_VALUES9(a, b, c, d, e, f, g, h, i) \
+  asm volatile("" : "+f"(a), "+f"(b), "+f"(c), "+f"(d), "+f"(e), "+f"(f), "+f"(g), "+f"(h), "+f"(i))
+#define M3_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
+#endif
 
 namespace m3 {
 
@@ -40,7 +50,9 @@ struct PointParams {
 struct PandaParams {
   float base[3], gravity;
   float q_lower[9], q_upper[9], qd_limit[9], effort[9];
-  float drive_damping, arm_inertia, finger_mass, robot_mu;
+  float drive_damping, finger_mass, robot_mu;
+  float joint_inertia[7];   // inertia the velocity drive of arm joint j works against
+  float warm_start, sleep_lin, sleep_ang, sleep_gap;
   float finger_half[3], finger_center[3], hand_half[3], hand_center[3];
   float contact_margin, baumgarte, slop, max_corr_vel, penalty_stiffness;
   float cube_half[2][3], cube_mass[2], cube_inertia[2], cube_mu[2];

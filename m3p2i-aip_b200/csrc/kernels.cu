@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "panda_env.cuh"
 #include "point_env.cuh"
+#include "rollout_common.cuh"
 
 namespace m3 {
 
@@ -31,142 +32,6 @@ DEV float env_cost(PandaEnv& e, const PandaParams& P, const RolloutCfg& c, int k
   if (ref) r = *ref;
   else { r.cube0[0] = e.cube[0].p.x; r.cube0[1] = e.cube[0].p.y; r.cube0[2] = e.cube[0].p.z; r.sel_axis = sel_axis_of(e.cube[0]); }
   return panda_cost(e, P, c, kg, r);
-}
-
-// Perturbed action of GLOBAL sample kg at step t (mppi.py:392-416). `kl` is its row in this shard's tables, or -1.
-// The planner sequences are read time-shifted by one step (MPPI._shift_action, mppi.py:266-273): the shift itself
-// is applied to the stored mean in k_finish.
-// mean + sigma * delta, clamp, mode / gripper / null-action overrides for given unit noise `delta` (mppi.py:392-416)
-template <int NU>
-DEV void perturb_action(const RolloutCfg& c, const RolloutBufs& b, int kg, int t, const float* delta_in, float* u) {
-  const int TN = c.T * NU, half = c.Kg / 2;
-  const int ts = c.preshifted ? t : min(t + 1, c.T - 1);
-  const float* mean = b.seq + (c.multi_modal ? (kg < half ? SEQ_MEAN1 : SEQ_MEAN2) : SEQ_MEAN) * TN + ts * NU;
-#pragma unroll
-  for (int d = 0; d < NU; ++d) {
-    const float delta = kg == c.Kg - 1 ? 0.0f : delta_in[d];
-    float v = mean[d] + delta * c.sigma[d];
-    v = fmaxf(fminf(v, c.u_max[d]), c.u_min[d]);
-    if (c.multi_modal) {
-      if (kg == 0) v = b.seq[SEQ_BEST1 * TN + ts * NU + d];
-      if (kg == half) v = b.seq[SEQ_BEST2 * TN + ts * NU + d];
-    }
-    if (NU == 9 && d >= 7) {
-      if (c.gripper == M3P2I_GRIPPER_OPEN) v = 1.5f;
-      else if (c.gripper == M3P2I_GRIPPER_CLOSE) v = -1.5f;
-    }
-    u[d] = c.u_scale * v;
-  }
-  if (c.null_action && kg == c.Kg - 1) {
-#pragma unroll
-    for (int d = 0; d < NU; ++d) u[d] = 0.0f;
-  }
-}
-
-template <int NU>
-DEV void sample_action(const RolloutCfg& c, const RolloutBufs& b, int kg, int kl, int t, float* u) {
-  const int K = c.K, TN = c.T * NU, half = c.Kg / 2;
-  if (c.open_loop) {
-#pragma unroll
-    for (int d = 0; d < NU; ++d) u[d] = c.u_scale * b.actions_in[(size_t)(t * NU + d) * K + kl];
-  } else {
-    const int ts = c.preshifted ? t : min(t + 1, c.T - 1);
-    const float* mean = b.seq + (c.multi_modal ? (kg < half ? SEQ_MEAN1 : SEQ_MEAN2) : SEQ_MEAN) * TN + ts * NU;
-    float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-    for (int d = 0; d < NU; ++d) {
-      float delta;
-      if (c.noise_mode != M3P2I_NOISE_TABLE) {
-        // the block that only feeds dim 8 is not drawn when the gripper command overrides the finger targets below
-        const bool unused = NU == 9 && d == 8 && (c.gripper == M3P2I_GRIPPER_OPEN || c.gripper == M3P2I_GRIPPER_CLOSE);
-        if ((d & 3) == 0 && !unused) noise4(c.noise_mode, c.seed_lo, c.seed_hi, (uint32_t)kg, t, c.T, (uint32_t)(d >> 2), z);
-        delta = z[d & 3];
-      } else if (kl >= 0) {
-        delta = b.noise ? b.noise[(size_t)(t * NU + d) * K + kl] : 0.0f;
-      } else {
-        delta = b.noise_row0 ? b.noise_row0[t * NU + d] : 0.0f;
-      }
-      if (kg == c.Kg - 1) delta = 0.0f;  // delta[-1] = 0: the mean itself is always a sample (mppi.py:392)
-      float v = mean[d] + delta * c.sigma[d];
-      v = fmaxf(fminf(v, c.u_max[d]), c.u_min[d]);
-      if (c.multi_modal) {
-        if (kg == 0) v = b.seq[SEQ_BEST1 * TN + ts * NU + d];
-        if (kg == half) v = b.seq[SEQ_BEST2 * TN + ts * NU + d];
-      }
-      if (NU == 9 && d >= 7) {
-        if (c.gripper == M3P2I_GRIPPER_OPEN) v = 1.5f;
-        else if (c.gripper == M3P2I_GRIPPER_CLOSE) v = -1.5f;
-      }
-      u[d] = c.u_scale * v;
-    }
-  }
-  if (c.null_action && kg == c.Kg - 1) {
-#pragma unroll
-    for (int d = 0; d < NU; ++d) u[d] = 0.0f;
-  }
-}
-
-// ------------------------------------------------------------------ rows 0 and Kg/2 of the batch (panda reach)
-// Every sample's reach cost reads, after each step, the cube position of sample 0 (cost_functions.py:98,102-103)
-// and the cube axis picked from the first row of the second half (skill_utils.py:275-279 on [half_samples:],
-// cost_functions.py:151-152). CTA 0 of the rollout grid is a PRODUCER: it replays those two rows (a shard that does
-// not own them reconstructs them from the planner state) and publishes refs[t] step by step; all other CTAs are
-// consumers that wait for step t before evaluating their cost. CTA 0 is dispatched first, so the producer is
-// resident before any consumer can spin, whatever the grid size.
-DEV void ref_publish(const RolloutBufs& b, int which, int t, unsigned epoch, const Cube& cubeA, bool with_axis) {
-  volatile PandaRef* r = b.refs + t;
-  if (which == 0) { r->cube0[0] = cubeA.p.x; r->cube0[1] = cubeA.p.y; r->cube0[2] = cubeA.p.z; }
-  if (which == 1 || with_axis) r->sel_axis = sel_axis_of(cubeA);
-  __threadfence();
-  *(volatile unsigned*)(b.ref_flags + which) = epoch + (unsigned)t + 1u;
-}
-DEV PandaRef ref_wait(const RolloutBufs& b, int t, unsigned epoch, bool two) {
-  const unsigned target = epoch + (unsigned)t + 1u;
-  while ((int)(*(volatile unsigned*)(b.ref_flags + 0) - target) < 0) {}
-  if (two) while ((int)(*(volatile unsigned*)(b.ref_flags + 1) - target) < 0) {}
-  __threadfence();
-  const volatile PandaRef* r = b.refs + t;
-  PandaRef out;
-  out.cube0[0] = r->cube0[0]; out.cube0[1] = r->cube0[1]; out.cube0[2] = r->cube0[2]; out.sel_axis = r->sel_axis;
-  return out;
-}
-
-// ------------------------------------------------------------------ all-gather of J fused into the rollout
-// Called by the one thread that owns sample k once its rollout is complete. System-scope fences order the remote
-// stores before the ticket and the ticket before the flags, so a peer that sees jflag == epoch sees every J.
-DEV void push_J(const PeerPush& p, int K, int offset, int k, float J) {
-  for (int r = 0; r < p.n; ++r) p.Jg[r][offset + k] = J;
-  __threadfence_system();
-  if (atomicAdd(p.ticket, 1u) == (unsigned)K - 1u) {
-    *p.ticket = 0u;   // the next launch on this stream starts from zero
-    __threadfence_system();
-    for (int r = 0; r < p.n; ++r) *(volatile unsigned*)(p.jflag[r] + p.rank) = p.epoch;
-  }
-}
-DEV void publish_J(const RolloutBufs& b, const RolloutCfg& c, int k, float J) {
-  b.J[k] = J;
-  if (b.peer.n) push_J(b.peer, c.K, c.offset, k, J);
-}
-
-// Threads 0..n-1 of the CTA poll one flag each until it reaches `epoch`; bounded, so that a peer that died cannot
-// hang this GPU (the command then reports M3P2I_ERR_STATE through *error).
-DEV unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-DEV void wait_flags(const unsigned* flags, int n, unsigned epoch, unsigned timeout_ms, unsigned* error) {
-  if ((int)threadIdx.x < n) {
-    const volatile unsigned* f = flags + threadIdx.x;
-    const unsigned long long t0 = global_ns(), limit = (unsigned long long)timeout_ms * 1000000ull;
-    unsigned polls = 0;
-    while ((int)(*f - epoch) < 0) {
-      if ((++polls & 1023u) == 0u && global_ns() - t0 > limit) { *error = 1u; break; }
-      __nanosleep(64);
-    }
-  }
-  __threadfence_system();
-  __syncthreads();
 }
 
 // ------------------------------------------------------------------ fused rollout
@@ -234,7 +99,7 @@ k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename
 
 }  // namespace m3
 
-#include "panda_team.cuh"   // needs sample_action / perturb_action / ref_publish / ref_wait from above
+#include "panda_team.cuh"
 
 namespace m3 {
 
@@ -243,20 +108,7 @@ namespace m3 {
 template <int CPL, int MINB>
 __global__ void __launch_bounds__(kTeamBlockMax, MINB)
 k_rollout_team(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
-  constexpr int TM = TeamShape<CPL>::kTeam;
-  const TeamLane t = team_lane<CPL>();
-  const bool use_refs = b.refs != nullptr;
-  const bool producer = use_refs && blockIdx.x == 0;
-  const int which = t.lane / TM;   // producer CTA: team 0 replays global row 0, team 1 global row Kg/2
-  const int kraw = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x + threadIdx.x) / TM;
-  const bool valid = !producer && kraw < c.K;
-  int k = kraw < c.K ? kraw : c.K - 1;   // idle teams shadow the last sample so that every shuffle has 32 lanes
-  int kg = c.offset + k;
-  if (producer) {
-    kg = (which == 1 && c.multi_modal) ? c.Kg / 2 : 0;
-    k = (kg >= c.offset && kg < c.offset + c.K) ? kg - c.offset : -1;
-  }
-  team_rollout<CPL>(c, P, b, t, k, kg, valid, producer, which);
+  team_kernel_body<CPL>(c, P, b);
 }
 
 // Threads per CTA of the rollout kernel. The kernel is latency-bound (one serial chain per sample), so small CTAs
@@ -319,10 +171,19 @@ void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, co
     const int tgrid = (c.K + teams_per_block - 1) / teams_per_block + extra;
     // MINB = 1: the whole grid is one CTA per SM, so the kernel may use the full register file (no spills)
     const bool one_wave = tgrid <= team_sms();
-    if (c.lanes == 16 && one_wave) k_rollout_team<1, 1><<<tgrid, tb, 0, st>>>(c, *qp, b);
-    else if (c.lanes == 16) k_rollout_team<1, 2><<<tgrid, tb, 0, st>>>(c, *qp, b);
-    else if (one_wave) k_rollout_team<2, 1><<<tgrid, tb, 0, st>>>(c, *qp, b);
-    else k_rollout_team<2, 2><<<tgrid, tb, 0, st>>>(c, *qp, b);
+    // dynamic shared memory: the contact accumulators of panda_team.cuh, 7 * CPL float4 per thread
+    const size_t smem = (size_t)7 * (16 / c.lanes) * sizeof(float4) * tb;
+    static bool attr_set = false;
+    if (!attr_set) {
+      const int max_smem = 7 * 2 * (int)sizeof(float4) * kTeamBlockMax;   // CPL = 2, largest CTA: above the 48 KB default
+      cudaFuncSetAttribute(k_rollout_team<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      cudaFuncSetAttribute(k_rollout_team<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      attr_set = true;
+    }
+    if (c.lanes == 16 && one_wave) k_rollout_team<1, 1><<<tgrid, tb, smem, st>>>(c, *qp, b);
+    else if (c.lanes == 16) k_rollout_team<1, 2><<<tgrid, tb, smem, st>>>(c, *qp, b);
+    else if (one_wave) k_rollout_team<2, 1><<<tgrid, tb, smem, st>>>(c, *qp, b);
+    else k_rollout_team<2, 2><<<tgrid, tb, smem, st>>>(c, *qp, b);
   } else {
     k_rollout<M3P2I_ENV_PANDA><<<grid, block, 0, st>>>(c, *qp, b);
   }

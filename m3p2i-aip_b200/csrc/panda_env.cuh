@@ -203,6 +203,67 @@ DEV V3 solve_contact3(Dyn3& A, Dyn3& B, V3 n, float depth, V3 c, float mu, float
   return Pn + Pt;
 }
 
+// Accumulated-impulse form of solve_contact3. `L` = (normal impulse, tangential impulse vector) the slot has applied
+// so far in this sub-step. The normal impulse is clamped on its running total (a later visit may take back what an
+// earlier one over-applied), the friction impulse is clamped to the Coulomb cone of the TOTAL normal impulse.
+// `first`: the slot's first visit in this sub-step; then `warm` tells whether the slot was in contact in the previous
+// sub-step of the same step(): if so P.warm_start times what it held (projected onto the tangent plane of the new
+// normal, inside the new cone) is re-applied before the solve, else the slot starts from zero.
+// Returns the impulse applied to A by this call.
+DEV V3 solve_contact3_acc(Dyn3& A, Dyn3& B, V3 n, float depth, V3 c, float mu, float h, const PandaParams& P, float4& L,
+                          bool first, bool warm) {
+  const V3 ra = c - A.x, rb = c - B.x;
+  V3 done = mk(0, 0, 0);
+  if (first) {
+    if (warm) {
+      const V3 lt0 = mk(L.y, L.z, L.w);
+      const float tn = dot(lt0, n);
+      const float ln = P.warm_start * L.x;
+      V3 lt = P.warm_start * (lt0 - tn * n);
+      const float lim = mu * ln, m2 = dot(lt, lt);
+      if (m2 > lim * lim) lt = (lim / sqrtf(m2)) * lt;
+      L = make_float4(ln, lt.x, lt.y, lt.z);
+      const V3 Pw = ln * n + lt;
+      apply_impulse(A, ra, Pw, 1.0f); apply_impulse(B, rb, Pw, -1.0f);
+      done = Pw;
+    } else {
+      L = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+  }
+  V3 rv = point_vel(A, ra) - point_vel(B, rb);
+  float vn = dot(rv, n);
+  const float kn = eff_mass(A, ra, n) + eff_mass(B, rb, n);
+  if (kn <= 0.0f) return done;
+  float target;
+  if (depth > 0.0f) {
+    const float pen = fmaxf(depth - P.slop, 0.0f);
+    target = fminf(P.baumgarte * pen / h, P.max_corr_vel);
+  } else {
+    target = depth / h;
+  }
+  const float ln = fmaxf(L.x + (target - vn) / kn, 0.0f);
+  const V3 Pn = (ln - L.x) * n;
+  L.x = ln;
+  apply_impulse(A, ra, Pn, 1.0f); apply_impulse(B, rb, Pn, -1.0f);
+  rv = point_vel(A, ra) - point_vel(B, rb);
+  vn = dot(rv, n);
+  V3 t = rv - vn * n;
+  const float vt2 = dot(t, t);
+  V3 lt = mk(L.y, L.z, L.w);
+  if (vt2 >= 1e-18f) {
+    const float vt = sqrtf(vt2);
+    t = (1.0f / vt) * t;
+    const float kt = eff_mass(A, ra, t) + eff_mass(B, rb, t);
+    if (kt > 0.0f) lt = lt - (vt / kt) * t;
+  }
+  const float lim = mu * ln, m2 = dot(lt, lt);
+  if (m2 > lim * lim) lt = (lim / sqrtf(m2)) * lt;
+  const V3 Pt = lt - mk(L.y, L.z, L.w);
+  L.y = lt.x; L.z = lt.y; L.w = lt.z;
+  apply_impulse(A, ra, Pt, 1.0f); apply_impulse(B, rb, Pt, -1.0f);
+  return done + Pn + Pt;
+}
+
 // The same contact equations for the hot pair type, a free cube against a fixed box: every term of the fixed body
 // vanishes, r x P is reused from r x n / r x t. Returns the impulse on the cube.
 DEV V3 solve_cube_static(V3& v, V3& w, float im, float ii, V3 x, V3 n, float depth, V3 c, float mu, float h,
@@ -330,42 +391,30 @@ DEV bool boxes_near(const OBox3& a, const OBox3& b, float margin) {
   return ex * ex + ey * ey + ez * ez <= ra * ra;
 }
 
-// Corner/SDF contact of the pair (A, ba) - (B, bb); the impulses received by B are added to accB.
-// BOTH: also test B's corners against A's box.
-template <bool BOTH>
-DEV void box_vs_box3(Dyn3& A, const OBox3& ba, Dyn3& B, const OBox3& bb, float mu, float h, const PandaParams& P, V3& accB) {
-  if (!boxes_near(ba, bb, P.contact_margin)) return;
+// Corners of box `ba` (body A) against box `bb` (body B), each hit solved as the pair (A, B) with the normal out of bb
+// -- or, FLIP, as the pair (B, A) with the normal reversed (the corners of the second body of a pair in the first).
+// `lam` = the 8 accumulator slots of this corner set (nullptr: plain solves), `prev` / `cur` = bit per corner: in
+// contact in the previous / this sub-step. Returns the impulse received by the FIRST body of the solved pair.
+template <bool FLIP>
+DEV V3 corners_vs_box3(Dyn3& A, const OBox3& ba, Dyn3& B, const OBox3& bb, float mu, float h, const PandaParams& P,
+                       float4* lam, unsigned prev, unsigned& cur, bool first) {
+  V3 got = mk(0, 0, 0);
   for (int i = 0; i < 8; ++i) {
     const V3 p = box_corner(ba, i);
     V3 n; float depth;
     if (!point_in_box(p, bb, P.contact_margin, n, depth)) continue;
-    accB = accB - solve_contact3(A, B, n, depth, p, mu, h, P);
-  }
-  if (BOTH) {
-    for (int i = 0; i < 8; ++i) {
-      const V3 p = box_corner(bb, i);
-      V3 n; float depth;
-      if (!point_in_box(p, ba, P.contact_margin, n, depth)) continue;
-      accB = accB - solve_contact3(A, B, -n, depth, p, mu, h, P);
+    cur |= 1u << i;
+    if (lam) {
+      const bool warm = (prev >> i) & 1u;
+      got = got + (FLIP ? solve_contact3_acc(B, A, -n, depth, p, mu, h, P, lam[i], first, warm)
+                        : solve_contact3_acc(A, B, n, depth, p, mu, h, P, lam[i], first, warm));
+    } else {
+      float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // no history: the plain one-shot solve
+      got = got + (FLIP ? solve_contact3_acc(B, A, -n, depth, p, mu, h, P, zero, false, false)
+                        : solve_contact3_acc(A, B, n, depth, p, mu, h, P, zero, false, false));
     }
   }
-}
-
-DEV void link_vs_cube(V3 lv, V3 lw, V3 lx, V3 axis, float& slide, float ims, const OBox3& lb, V3& v, V3& w, float im,
-                      float ii, V3 x, const OBox3& cb, float mu, float h, const PandaParams& P, V3& accC) {
-  if (!boxes_near(lb, cb, P.contact_margin)) return;
-  for (int i = 0; i < 8; ++i) {   // corners of the link in the cube, normal out of the cube
-    const V3 p = box_corner(lb, i);
-    V3 n; float depth;
-    if (!point_in_box(p, cb, P.contact_margin, n, depth)) continue;
-    accC = accC - solve_link_cube(lv, lw, lx, axis, slide, ims, v, w, im, ii, x, n, depth, p, mu, h, P);
-  }
-  for (int i = 0; i < 8; ++i) {   // corners of the cube in the link, normal out of the link
-    const V3 p = box_corner(cb, i);
-    V3 n; float depth;
-    if (!point_in_box(p, lb, P.contact_margin, n, depth)) continue;
-    accC = accC - solve_link_cube(lv, lw, lx, axis, slide, ims, v, w, im, ii, x, -n, depth, p, mu, h, P);
-  }
+  return got;
 }
 
 // kinematic link box against a fixed box: penalty force on the fixed body (reported to the collision cost only)
@@ -386,16 +435,23 @@ DEV void link_vs_static(const OBox3& lb, const Dyn3& L, const OBox3& sb, float m
   }
 }
 
+// One step() of the integrator, one thread per environment (the sim facade, the producer of the thread-per-sample
+// rollout kernel and that kernel itself). Restated lane-cooperatively in panda_team.cuh.
 DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt, int substeps, int passes) {
   const float h = dt / (float)substeps;
   const float D = P.drive_damping;
   V3 imp_table = mk(0, 0, 0), imp_shelf = mk(0, 0, 0), imp_cubeb = mk(0, 0, 0);
   V3 pen_table = mk(0, 0, 0), pen_shelf = mk(0, 0, 0);
+  // accumulated contact impulses of the current sub-step, kept for the warm start of the next one (a step() starts
+  // cold). Slots: [0,16) cube i vs its first near fixed box; [16,32) cube/cube (corners of A in B, of B in A);
+  // 32 + 32 f + 16 i + 8 ph: link f vs cube i (ph 0: link corners in the cube, 1: cube corners in the link).
+  float4 lam[128];
+  unsigned prev[4] = {0u, 0u, 0u, 0u};   // bit per slot: in contact in the previous sub-step
   for (int s = 0; s < substeps; ++s) {
     // 1. joint drives: implicit velocity tracking, effort- and speed-limited, no motion into a joint limit
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
-      const float m = j < 7 ? P.arm_inertia : P.finger_mass;
+      const float m = j < 7 ? P.joint_inertia[j < 7 ? j : 0] : P.finger_mass;
       const float v = e.qd[j];
       float vs = (m * v + h * D * u[j]) / (m + h * D);
       const float f = D * (u[j] - vs);
@@ -406,10 +462,7 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
       if (e.q[j] >= P.q_upper[j] && vs > 0.0f) vs = 0.0f;
       e.qd[j] = vs;
     }
-    // 2. gravity
-    e.cube[0].v.z -= P.gravity * h;
-    e.cube[1].v.z -= P.gravity * h;
-    // 3. contacts
+    // link and cube boxes of this sub-step (positions are fixed until step 5)
     Hand H;
     panda_hand(P, e.q, e.qd, true, H);
     OBox3 lbox[3];
@@ -442,63 +495,92 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
       C[i].im = 1.0f / P.cube_mass[i]; C[i].ii = 1.0f / P.cube_inertia[i];
       C[i].axis = mk(0, 0, 0); C[i].slide = 0.0f; C[i].ims = 0.0f;
     }
-    // Positions are fixed during a sub-step, so which cube corners touch which fixed box is decided once (pass 0)
-    // and remembered as one bit per (fixed box, corner); later passes revisit only those corners.
-    unsigned long long hit[2] = {0ull, 0ull};
-    unsigned lnear = 0u;
-    for (int p = 0; p < passes; ++p) {
+    // what is close to what, decided once per sub-step: link f / cube i (bit 2 f + i), fixed boxes per cube
+    const bool cc_near = boxes_near(cbox[0], cbox[1], P.contact_margin);
+    unsigned lnear = 0u, snear[2] = {0u, 0u};
+    int first_box[2] = {-1, -1};
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
-        for (int k = 0; k < P.n_static; ++k) {
-          unsigned m;
-          if (p == 0) {
-            m = 0u;
-            const OBox3 sb = obox_of(P.st[k]);
-            if (boxes_near(cbox[i], sb, P.contact_margin)) m = 0xffu;
-          } else {
-            m = (unsigned)(hit[i] >> (8 * k)) & 0xffu;
-          }
-          if (!m) continue;
-          const OBox3 sb = obox_of(P.st[k]);
-          const float mu = 0.5f * (P.cube_mu[i] + P.st[k].mu);
-          V3 accS = mk(0, 0, 0);
-          unsigned found = 0u;
-          for (int c = 0; c < 8; ++c) {
-            if (!((m >> c) & 1u)) continue;
-            const V3 pt = box_corner(cbox[i], c);
-            V3 n; float depth;
-            if (!point_in_box(pt, sb, P.contact_margin, n, depth)) continue;
-            found |= 1u << c;
-            accS = accS - solve_cube_static(C[i].v, C[i].w, C[i].im, C[i].ii, C[i].x, n, depth, pt, mu, h, P);
-          }
-          if (p == 0) hit[i] |= (unsigned long long)found << (8 * k);
-          if (k == P.idx_table && P.report_cube) imp_table = imp_table + accS;
-          if (k == P.idx_shelf && P.report_cube) imp_shelf = imp_shelf + accS;
-          if (i == 1) imp_cubeb = imp_cubeb - accS;
-        }
-      box_vs_box3<true>(C[0], cbox[0], C[1], cbox[1], 0.5f * (P.cube_mu[0] + P.cube_mu[1]), h, P, imp_cubeb);
-      // the finger - cube - finger chain of a grasp settles only after a few sweeps over its own contacts; which
-      // link / cube pairs are close is decided once per sub-step (bit 2 f + i), most rollouts have none
-      if (p == 0) {
-        lnear = 0u;
+    for (int i = 0; i < 2; ++i) {
 #pragma unroll
-        for (int f = 0; f < 3; ++f)
+      for (int f = 0; f < 3; ++f)
+        if (boxes_near(lbox[f], cbox[i], P.contact_margin)) lnear |= 1u << (2 * f + i);
+      for (int k = 0; k < P.n_static; ++k)
+        if (boxes_near(cbox[i], obox_of(P.st[k]), P.contact_margin)) { snear[i] |= 1u << k; if (first_box[i] < 0) first_box[i] = k; }
+    }
+    // 2. sleeping: an (almost) motionless cube that rests on its first near fixed box with at least three corners and
+    // has no link and no other cube within the contact margin is neither moved nor solved in this sub-step
+    bool asleep[2] = {false, false};
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
-            if (boxes_near(lbox[f], cbox[i], P.contact_margin)) lnear |= 1u << (2 * f + i);
+    for (int i = 0; i < 2; ++i) {
+      if (!(P.sleep_lin > 0.0f)) continue;
+      const Cube& c = e.cube[i];
+      if (!(dot(c.v, c.v) < P.sleep_lin * P.sleep_lin && dot(c.w, c.w) < P.sleep_ang * P.sleep_ang)) continue;
+      if (cc_near || ((lnear >> i) & 0x15u) || first_box[i] < 0) continue;
+      const OBox3 sb = obox_of(P.st[first_box[i]]);
+      int cnt = 0;
+      for (int ci = 0; ci < 8; ++ci) {
+        V3 n; float depth;
+        if (point_in_box(box_corner(cbox[i], ci), sb, P.contact_margin, n, depth) && depth > -P.sleep_gap) ++cnt;
       }
-      for (int sw = 0; sw < P.link_sweeps && lnear; ++sw)
+      if (cnt < 3) continue;
+      asleep[i] = true;
+      e.cube[i].v = mk(0, 0, 0); e.cube[i].w = mk(0, 0, 0);
+      C[i].v = mk(0, 0, 0); C[i].w = mk(0, 0, 0);
+      const float wgt = P.cube_mass[i] * P.gravity * h;   // the support carries the weight
+      if (first_box[i] == P.idx_table && P.report_cube) imp_table.z -= wgt;
+      if (first_box[i] == P.idx_shelf && P.report_cube) imp_shelf.z -= wgt;
+      if (i == 1) imp_cubeb.z += wgt;
+    }
+    // 3. gravity
 #pragma unroll
-      for (int f = 0; f < 3; ++f) {
-        V3 sink = mk(0, 0, 0);
-        if ((lnear >> (2 * f)) & 1u)
-          link_vs_cube(L[f].v, L[f].w, L[f].x, L[f].axis, L[f].slide, L[f].ims, lbox[f], C[0].v, C[0].w, C[0].im, C[0].ii,
-                       C[0].x, cbox[0], 0.5f * (P.robot_mu + P.cube_mu[0]), h, P, sink);
-        if ((lnear >> (2 * f + 1)) & 1u)
-          link_vs_cube(L[f].v, L[f].w, L[f].x, L[f].axis, L[f].slide, L[f].ims, lbox[f], C[1].v, C[1].w, C[1].im, C[1].ii,
-                       C[1].x, cbox[1], 0.5f * (P.robot_mu + P.cube_mu[1]), h, P, imp_cubeb);
+    for (int i = 0; i < 2; ++i) if (!asleep[i]) C[i].v.z -= P.gravity * h;
+    // 4. contacts. Every pass: links (link_sweeps sweeps: the finger - cube - finger chain of a grasp) and cube/cube
+    // first, the fixed boxes LAST (what a kinematic link pushes into the table is pushed back out in the same pass).
+    unsigned cur[4] = {0u, 0u, 0u, 0u};
+    for (int p = 0; p < passes; ++p) {
+      for (int sw = 0; sw < P.link_sweeps && lnear; ++sw) {
+        const bool first = p == 0 && sw == 0;
+        for (int f = 0; f < 3; ++f)
+          for (int i = 0; i < 2; ++i) {
+            if (asleep[i] || !((lnear >> (2 * f + i)) & 1u)) continue;
+            const float mu = 0.5f * (P.robot_mu + P.cube_mu[i]);
+            const int s0 = 32 + 32 * f + 16 * i;
+            unsigned c0 = 0u, c1 = 0u;
+            V3 got = corners_vs_box3<false>(L[f], lbox[f], C[i], cbox[i], mu, h, P, lam + s0, (prev[s0 >> 5] >> (s0 & 31)) & 0xffu, c0, first);
+            got = got + corners_vs_box3<true>(C[i], cbox[i], L[f], lbox[f], mu, h, P, lam + s0 + 8, (prev[s0 >> 5] >> ((s0 & 31) + 8)) & 0xffu, c1, first);
+            cur[s0 >> 5] |= (c0 | (c1 << 8)) << (s0 & 31);
+            if (i == 1) imp_cubeb = imp_cubeb - got;   // `got` = impulse on the link; cubeB received the opposite
+          }
+      }
+      if (cc_near) {
+        const float mu = 0.5f * (P.cube_mu[0] + P.cube_mu[1]);
+        unsigned c0 = 0u, c1 = 0u;
+        V3 got = corners_vs_box3<false>(C[0], cbox[0], C[1], cbox[1], mu, h, P, lam + 16, (prev[0] >> 16) & 0xffu, c0, p == 0);
+        got = got + corners_vs_box3<true>(C[1], cbox[1], C[0], cbox[0], mu, h, P, lam + 24, (prev[0] >> 24) & 0xffu, c1, p == 0);
+        cur[0] |= (c0 << 16) | (c1 << 24);
+        imp_cubeb = imp_cubeb - got;                   // `got` = impulse on cubeA
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (asleep[i]) continue;
+        for (unsigned todo = snear[i]; todo; todo &= todo - 1) {
+          const int k = __ffs(todo) - 1;
+          const OBox3 sb = obox_of(P.st[k]);
+          Dyn3 S;
+          S.v = mk(0, 0, 0); S.w = mk(0, 0, 0); S.x = sb.c; S.im = 0.0f; S.ii = 0.0f; S.axis = mk(0, 0, 0); S.slide = 0.0f; S.ims = 0.0f;
+          const bool acc = k == first_box[i];
+          unsigned c0 = 0u;
+          const V3 got = corners_vs_box3<false>(C[i], cbox[i], S, sb, 0.5f * (P.cube_mu[i] + P.st[k].mu), h, P,
+                                                acc ? lam + 8 * i : nullptr, (prev[0] >> (8 * i)) & 0xffu, c0, p == 0);
+          if (acc) cur[0] |= c0 << (8 * i);
+          if (k == P.idx_table && P.report_cube) imp_table = imp_table - got;
+          if (k == P.idx_shelf && P.report_cube) imp_shelf = imp_shelf - got;
+          if (i == 1) imp_cubeb = imp_cubeb + got;
+        }
       }
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) prev[q] = cur[q];
 #pragma unroll
     for (int i = 0; i < 2; ++i) { e.cube[i].v = C[i].v; e.cube[i].w = C[i].w; }
 #pragma unroll
@@ -514,7 +596,7 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
       if (P.idx_shelf >= 0)
         link_vs_static(lbox[f], L[f], obox_of(P.st[P.idx_shelf]), 0.5f * (P.robot_mu + P.st[P.idx_shelf].mu), P, pen_shelf);
     }
-    // 4. positions
+    // 5. positions
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
       float qn = e.q[j] + h * e.qd[j];
@@ -524,6 +606,7 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
+      if (asleep[i]) continue;
       Cube& c = e.cube[i];
       c.p = c.p + h * c.v;
       const float x = c.qx, y = c.qy, z = c.qz, w = c.qw, hh = 0.5f * h;

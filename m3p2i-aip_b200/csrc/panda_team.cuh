@@ -25,7 +25,7 @@
 // of step t is evaluated from the hand pose of the first sub-step of step t+1 — same joint positions), link / cube
 // pairs, the two detection directions and the corner slots as rolled loops, one inlined copy of each contact solve.
 #pragma once
-#include "panda_env.cuh"
+#include "rollout_common.cuh"
 
 namespace m3 {
 
@@ -120,8 +120,15 @@ struct TeamEnv {
 
 // The generic two-body solve is only reached when the two cubes touch each other; one out-of-line copy.
 __device__ __noinline__ V3 solve_contact3_call(Dyn3& A, Dyn3& B, V3 n, float depth, V3 c, float mu, float h,
-                                               const PandaParams& P) {
-  return solve_contact3(A, B, n, depth, c, mu, h, P);
+                                               const PandaParams& P, float4& L, bool first) {
+  // the slot's warm start was prepared by its owner (warm_prepare): `first` only has to apply it
+  V3 done = mk(0, 0, 0);
+  if (first) {
+    const V3 Pw = L.x * n + mk(L.y, L.z, L.w);
+    apply_impulse(A, c - A.x, Pw, 1.0f); apply_impulse(B, c - B.x, Pw, -1.0f);
+    done = Pw;
+  }
+  return done + solve_contact3_acc(A, B, n, depth, c, mu, h, P, L, false, false);
 }
 
 DEV Dyn3 dyn_cube(V3 v, V3 w, V3 x, float im, float ii) {
@@ -131,11 +138,17 @@ DEV Dyn3 dyn_cube(V3 v, V3 w, V3 x, float im, float ii) {
 }
 
 // Serial application of the contacts found by the G lanes [src0, src0+G): for lane j = 0..G-1 in order, the lane
-// that found a hit broadcasts (n, depth, p) and every lane for which `mine` holds applies solve(n, depth, p).
-// Returns the sum of the impulses the solves report. The loop bounds and the shuffles are warp-uniform.
+// that found a hit broadcasts (n, depth, p) together with its accumulator slot L and every lane for which `mine` holds
+// applies solve(n, depth, p, L); the lane that owns the slot keeps the updated L. Returns the sum of the impulses the
+// solves report. The loop bounds and the shuffles are warp-uniform.
+DEV float4 shfl4(float4 a, int src) {
+  return make_float4(__shfl_sync(kFull, a.x, src), __shfl_sync(kFull, a.y, src), __shfl_sync(kFull, a.z, src),
+                     __shfl_sync(kFull, a.w, src));
+}
 template <int G, typename Solve>
-DEV V3 apply_hits(bool hit, V3 n, float depth, V3 p, int src0, bool mine, Solve&& solve) {
+DEV V3 apply_hits(bool hit, V3 n, float depth, V3 p, float4& L, int src0, bool mine, Solve&& solve) {
   const unsigned hb = __ballot_sync(kFull, hit);
+  const int lane = threadIdx.x & 31;
   V3 acc = mk(0, 0, 0);
   // lanes that hit in ANY group of the warp, visited in ascending order
   unsigned todo = fold<G>(hb);
@@ -146,7 +159,11 @@ DEV V3 apply_hits(bool hit, V3 n, float depth, V3 p, int src0, bool mine, Solve&
     const bool act = mine && ((hb >> src) & 1u);
     const V3 nj = shfl3(n, src), pj = shfl3(p, src);
     const float dj = __shfl_sync(kFull, depth, src);
-    if (act) acc = acc + solve(nj, dj, pj);
+    float4 Lj = shfl4(L, src);
+    if (act) {
+      acc = acc + solve(nj, dj, pj, Lj);
+      if (lane == src) L = Lj;
+    }
   }
   return acc;
 }
@@ -156,7 +173,7 @@ DEV V3 apply_hits(bool hit, V3 n, float depth, V3 p, int src0, bool mine, Solve&
 // normal speed) is worked out ONCE, by all corner lanes in parallel, and only the velocity-dependent part of
 // solve_cube_static is left in the serial Gauss-Seidel chain.
 struct StaticHit {
-  bool hit;
+  bool hit, sup;   // sup: the corner is within sleep_gap of the box (it supports the cube)
   V3 n, rn;
   float ikn, target;
 };
@@ -166,17 +183,37 @@ DEV StaticHit static_hit(bool near, V3 pc, V3 ra, const OBox3& sb, float im, flo
   s.n = mk(0, 0, 0);
   float depth = 0.0f;
   s.hit = near && point_in_box(pc, sb, P.contact_margin, s.n, depth);
+  s.sup = s.hit && depth > -P.sleep_gap;
   s.rn = cross(ra, s.n);
   s.ikn = __fdividef(1.0f, im + ii * dot(s.rn, s.rn));
   s.target = depth > 0.0f ? fminf(P.baumgarte * fmaxf(depth - P.slop, 0.0f) * inv_h, P.max_corr_vel) : depth * inv_h;
   return s;
 }
 
-// Serial application (ascending corner order, as apply_hits) of the fixed-box contacts of the own cube: the same
-// equations as solve_cube_static with the geometry terms taken from the StaticHit of the lane that found the contact.
+// The warm start of an accumulator slot, prepared by the lane that owns it before the serial chain starts: what the
+// slot held in the previous sub-step (if it was in contact then), scaled, projected onto the tangent plane of the new
+// normal and clamped to the new cone -- or zero. The serial chain then just applies it at the slot's first visit.
+DEV float4 warm_prepare(float4 L, bool warm, V3 n, float mu, float k) {
+  if (!warm) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  const V3 lt0 = mk(L.y, L.z, L.w);
+  const float tn = dot(lt0, n);
+  const float ln = k * L.x;
+  V3 lt = k * (lt0 - tn * n);
+  const float lim = mu * ln, m2 = dot(lt, lt);
+  if (m2 > lim * lim) lt = (lim * rsqrtf(m2)) * lt;
+  return make_float4(ln, lt.x, lt.y, lt.z);
+}
+
+// Serial application (ascending corner order, as apply_hits) of the fixed-box contacts of the own cube: the equations
+// of solve_contact3_acc for a free cube against a fixed body, with the geometry terms taken from the StaticHit of the
+// lane that found the contact. `L` = this lane's accumulator for the slot (prepared by warm_prepare when `first`);
+// `keep` = the slot accumulates over visits (the cube's first near fixed box); otherwise every visit starts from zero,
+// which is the plain one-shot solve.
 template <int G>
-DEV V3 apply_static_hits(const StaticHit& s, V3 ra, int group_base, V3& v, V3& w, float im, float ii, float mu) {
+DEV V3 apply_static_hits(const StaticHit& s, V3 ra, int group_base, V3& v, V3& w, float im, float ii, float mu, float4& L,
+                         bool keep, bool first) {
   const unsigned hb = __ballot_sync(kFull, s.hit);
+  const int lane = threadIdx.x & 31;
   V3 acc = mk(0, 0, 0);
   unsigned todo = fold<G>(hb);
   while (todo) {
@@ -185,26 +222,38 @@ DEV V3 apply_static_hits(const StaticHit& s, V3 ra, int group_base, V3& v, V3& w
     const int src = group_base + j;
     const V3 n = shfl3(s.n, src), rn = shfl3(s.rn, src), r = shfl3(ra, src);
     const float ikn = __shfl_sync(kFull, s.ikn, src), target = __shfl_sync(kFull, s.target, src);
-    const float jn = (target - (dot(v, n) + dot(w, rn))) * ikn;
-    if (((hb >> src) & 1u) && jn > 0.0f) {
-      v = v + (jn * im) * n;
-      w = w + (jn * ii) * rn;
-      const V3 va = v + cross(w, r);
-      const float vn = dot(va, n);
-      V3 t = va - vn * n;
-      const float vt2 = dot(t, t);
-      acc = acc + jn * n;
-      if (vt2 >= 1e-18f) {
-        const float ivt = rsqrtf(vt2), vt = vt2 * ivt;
-        t = ivt * t;
-        const V3 rt = cross(r, t);
-        const float kt = im + ii * dot(rt, rt);
-        const float jt = fminf(__fdividef(vt, kt), mu * jn);
-        v = v - (jt * im) * t;
-        w = w - (jt * ii) * rt;
-        acc = acc - jt * t;
-      }
+    float4 Lj = shfl4(L, src);
+    if (!((hb >> src) & 1u)) continue;
+    if (!keep) Lj = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (first && keep) {
+      const V3 Pw = Lj.x * n + mk(Lj.y, Lj.z, Lj.w);
+      v = v + im * Pw;
+      w = w + ii * cross(r, Pw);
+      acc = acc + Pw;
     }
+    const float ln = fmaxf(Lj.x + (target - (dot(v, n) + dot(w, rn))) * ikn, 0.0f);
+    const float dj = ln - Lj.x;
+    v = v + (dj * im) * n;
+    w = w + (dj * ii) * rn;
+    const V3 va = v + cross(w, r);
+    const float vn = dot(va, n);
+    V3 t = va - vn * n;
+    const float vt2 = dot(t, t);
+    V3 lt = mk(Lj.y, Lj.z, Lj.w);
+    if (vt2 >= 1e-18f) {
+      const float ivt = rsqrtf(vt2), vt = vt2 * ivt;
+      t = ivt * t;
+      const V3 rt = cross(r, t);
+      const float kt = im + ii * dot(rt, rt);
+      lt = lt - __fdividef(vt, kt) * t;
+    }
+    const float lim = mu * ln, m2 = dot(lt, lt);
+    if (m2 > lim * lim) lt = (lim * rsqrtf(m2)) * lt;
+    const V3 Pt = lt - mk(Lj.y, Lj.z, Lj.w);
+    v = v + im * Pt;
+    w = w + ii * cross(r, Pt);
+    acc = acc + dj * n + Pt;
+    if (keep && lane == src) L = make_float4(ln, lt.x, lt.y, lt.z);
   }
   return acc;
 }
@@ -233,10 +282,12 @@ DEV LinkHit link_hit(bool hit, V3 n, float depth, V3 pt, V3 hv, V3 hw, V3 hp, V3
 }
 
 // Serial application of the link contacts found by lanes [src0, src0+G) (hb = warp ballot of s.hit); returns the sum
-// of the impulses on the link.
+// of the impulses on the link. The equations of solve_contact3_acc for a kinematic link (one sliding DoF for a finger)
+// against a free cube; `L` = this lane's accumulator of the slot (prepared by warm_prepare when `first`).
 template <int G>
 DEV V3 apply_link_hits(const LinkHit& s, unsigned hb, int src0, bool mine, V3 axis, float& slide, float ims, V3& v, V3& w,
-                       float im, float ii, float mu) {
+                       float im, float ii, float mu, float4& L, bool first) {
+  const int lane = threadIdx.x & 31;
   V3 acc = mk(0, 0, 0);
   unsigned todo = fold<G>(hb);
   while (todo) {
@@ -246,30 +297,42 @@ DEV V3 apply_link_hits(const LinkHit& s, unsigned hb, int src0, bool mine, V3 ax
     const V3 n = shfl3(s.n, src), rcn = shfl3(s.rcn, src), rc = shfl3(s.rc, src), vl0 = shfl3(s.vl0, src);
     const float an = __shfl_sync(kFull, s.an, src), ikn = __shfl_sync(kFull, s.ikn, src);
     const float target = __shfl_sync(kFull, s.target, src);
-    const float vn0 = dot(vl0, n) + slide * an - (dot(v, n) + dot(w, rcn));
-    const float jn = (target - vn0) * ikn;
-    if (mine && ((hb >> src) & 1u) && jn > 0.0f) {
-      slide += ims * an * jn;
-      v = v - (jn * im) * n;
-      w = w - (jn * ii) * rcn;
-      const V3 rv = (vl0 + slide * axis) - (v + cross(w, rc));
-      const float vn = dot(rv, n);
-      V3 t = rv - vn * n;
-      const float vt2 = dot(t, t);
-      acc = acc + jn * n;
-      if (vt2 >= 1e-18f) {
-        const float ivt = rsqrtf(vt2), vt = vt2 * ivt;
-        t = ivt * t;
-        const V3 rct = cross(rc, t);
-        const float at = dot(axis, t);
-        const float kt = ims * at * at + im + ii * dot(rct, rct);
-        const float jt = fminf(__fdividef(vt, kt), mu * jn);
-        slide -= ims * at * jt;
-        v = v + (jt * im) * t;
-        w = w + (jt * ii) * rct;
-        acc = acc - jt * t;
-      }
+    const float4 Lj = shfl4(L, src);
+    if (!(mine && ((hb >> src) & 1u))) continue;
+    if (first) {
+      const V3 Pw = Lj.x * n + mk(Lj.y, Lj.z, Lj.w);   // on the link; the cube receives -Pw
+      slide += ims * dot(axis, Pw);
+      v = v - im * Pw;
+      w = w - ii * cross(rc, Pw);
+      acc = acc + Pw;
     }
+    const float vn0 = dot(vl0, n) + slide * an - (dot(v, n) + dot(w, rcn));
+    const float ln = fmaxf(Lj.x + (target - vn0) * ikn, 0.0f);
+    const float dj = ln - Lj.x;
+    slide += ims * an * dj;
+    v = v - (dj * im) * n;
+    w = w - (dj * ii) * rcn;
+    const V3 rv = (vl0 + slide * axis) - (v + cross(w, rc));
+    const float vn = dot(rv, n);
+    V3 t = rv - vn * n;
+    const float vt2 = dot(t, t);
+    V3 lt = mk(Lj.y, Lj.z, Lj.w);
+    if (vt2 >= 1e-18f) {
+      const float ivt = rsqrtf(vt2), vt = vt2 * ivt;
+      t = ivt * t;
+      const V3 rct = cross(rc, t);
+      const float at = dot(axis, t);
+      const float kt = ims * at * at + im + ii * dot(rct, rct);
+      lt = lt - __fdividef(vt, kt) * t;
+    }
+    const float lim = mu * ln, m2 = dot(lt, lt);
+    if (m2 > lim * lim) lt = (lim * rsqrtf(m2)) * lt;
+    const V3 Pt = lt - mk(Lj.y, Lj.z, Lj.w);
+    slide += ims * dot(axis, Pt);
+    v = v - im * Pt;
+    w = w - ii * cross(rc, Pt);
+    acc = acc + dj * n + Pt;
+    if (lane == src) L = make_float4(ln, lt.x, lt.y, lt.z);
   }
   return acc;
 }
@@ -339,12 +402,23 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
   float qo = e.q[0], vo = e.qd[0];
 #pragma unroll
   for (int i = 1; i < 7; ++i) { if (jo == i) { qo = e.q[i]; vo = e.qd[i]; } }
-  const float lo_o = P.q_lower[jo], up_o = P.q_upper[jo], vl_o = P.qd_limit[jo], ef_o = P.effort[jo];
+  const float lo_o = P.q_lower[jo], up_o = P.q_upper[jo], vl_o = P.qd_limit[jo], ef_o = P.effort[jo], m_o = P.joint_inertia[jo];
   Hand Hl;          // hand pose + twist of iteration blk0 + t.tl
   float ul[NU];     // action of the step of iteration blk0 + t.tl
 #pragma unroll
   for (int d = 0; d < NU; ++d) ul[d] = 0.0f;
   float uf[2] = {0.0f, 0.0f};   // finger velocity targets of the current step
+  // accumulated contact impulses, kept from one sub-step to the next inside a step() for the warm start
+  // (solve_contact3_acc): own corners against the support box in registers; the link / cube (slot f * 2 CPL + phs)
+  // and cube / cube (slot 6 CPL + sl) contacts of this lane in shared memory, [slot][thread]
+  float4 lam_st[CPL];
+#pragma unroll
+  for (int sl = 0; sl < CPL; ++sl) lam_st[sl] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  unsigned prev_st = 0u, prev_lk = 0u, prev_cc = 0u;   // bit per slot: in contact in the previous sub-step
+  M3_DYNAMIC_SMEM(float4, slam_base);
+  float4* const slam = slam_base + threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < 7 * CPL; ++q) slam[q * blockDim.x] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 
   const int n_iter = T * ns;
 #pragma unroll 1
@@ -382,7 +456,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
         for (int i = 0; i < 7; ++i) { const float v = __shfl_sync(kFull, ul[i], src); if (jo == i) uj = v; }
         if (!lasti) {
           // 1. joint drive of the own joint
-          const float m = P.arm_inertia;
+          const float m = m_o;
           float vs = (m * vo + h * D * uj) / (m + h * D);
           const float f = D * (uj - vs);
           if (f > ef_o) vs = vo + h * ef_o / m;
@@ -467,9 +541,8 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     }
     if (last) break;
 
-    // ---- 2. gravity on the group's cube
-    e.cu.v.z -= P.gravity * h;
-    // ---- 3. geometry of this sub-step (positions are fixed until step 4)
+    // ---- 2. geometry of this sub-step (positions are fixed until step 5)
+    if (s == 0) { prev_st = 0u; prev_lk = 0u; prev_cc = 0u; }   // a step() starts cold (no warm start across steps)
     V3 lc[3];  // centres of the left-finger, right-finger and hand boxes
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
@@ -487,8 +560,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     cb.c = e.cu.p; cb.R = quat_to_R(e.cu.qx, e.cu.qy, e.cu.qz, e.cu.qw); cb.half = half_own;
     // keep the nine entries as values: under register pressure ptxas otherwise re-derives them from the quaternion
     // inside the contact loops (26 instructions per use, 12 % of all instructions in a grasp state)
-    asm volatile("" : "+f"(cb.R.cx.x), "+f"(cb.R.cx.y), "+f"(cb.R.cx.z), "+f"(cb.R.cy.x), "+f"(cb.R.cy.y), "+f"(cb.R.cy.z),
-                      "+f"(cb.R.cz.x), "+f"(cb.R.cz.y), "+f"(cb.R.cz.z));
+    M3_PIN_VALUES9(cb.R.cx.x, cb.R.cx.y, cb.R.cx.z, cb.R.cy.x, cb.R.cy.y, cb.R.cy.z, cb.R.cz.x, cb.R.cz.y, cb.R.cz.z);
     V3 v = e.cu.v, w = e.cu.w;
     const V3 x = e.cu.p;
     // own corners, as lever arms about the cube centre (corner = x + ra); slot s is corner t.c + s * G
@@ -512,14 +584,14 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     }
     // which fixed boxes / link boxes are close to the own cube, decided once per sub-step:
     // lane c of a group tests fixed boxes c, c + G, ... (n_static <= 8); one ballot per slot collects the verdicts
-    unsigned near_mask = 0u, near_any = 0u;
+    unsigned near_mask = 0u;
+    bool near_c[CPL];
 #pragma unroll
     for (int sl = 0; sl < CPL; ++sl) {
       const int kb = t.c + sl * G;
-      const bool near_c = kb < P.n_static && boxes_near(cb, obox_of(P.st[min(kb, P.n_static - 1)]), P.contact_margin);
-      const unsigned bal = __ballot_sync(kFull, near_c);
+      near_c[sl] = kb < P.n_static && boxes_near(cb, obox_of(P.st[min(kb, P.n_static - 1)]), P.contact_margin);
+      const unsigned bal = __ballot_sync(kFull, near_c[sl]);
       near_mask |= ((bal >> t.group_base) & ((1u << G) - 1u)) << (sl * G);
-      near_any |= fold<G>(bal) << (sl * G);
     }
     unsigned lnear = 0u;
 #pragma unroll 1
@@ -532,76 +604,63 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       if (dot(dl, dl) > rr * rr) continue;
       if (boxes_near(lb, cb, P.contact_margin)) lnear |= 1u << f;
     }
-    // geometry-only part of the own corners' contacts with the first near fixed box (see StaticHit); it is almost
-    // always the only one (the table), so the passes below reuse it
+    // geometry-only part of the own corners' contacts with the cube's FIRST near fixed box, its support (StaticHit):
+    // these are the contacts that keep accumulators; the passes below reuse them
     const float inv_h = __frcp_rn(h);
-    const int ks0 = near_any ? __ffs(near_any) - 1 : 0;
-    unsigned live = 0xffffffu;  // link contact slots (pair fi, direction/slot phs) not yet known to be empty
+    const int k0 = near_mask ? __ffs(near_mask) - 1 : 0;
     StaticHit sh0[CPL];
     {
-      const OBox3 sb = obox_of(P.st[ks0]);
-      const bool near0 = near_any && ((near_mask >> ks0) & 1u);
+      const OBox3 sb = obox_of(P.st[k0]);
 #pragma unroll
-      for (int sl = 0; sl < CPL; ++sl) sh0[sl] = static_hit(near0, x + ra[sl], ra[sl], sb, im, ii, inv_h, P);
+      for (int sl = 0; sl < CPL; ++sl) sh0[sl] = static_hit(near_mask != 0u, x + ra[sl], ra[sl], sb, im, ii, inv_h, P);
     }
+    // ---- 3. sleeping (decided per cube, i.e. per group): an (almost) motionless cube that rests on its first near
+    // fixed box with at least three corners and has no link and no other cube within the contact margin is neither
+    // moved nor solved in this sub-step
+    bool asleep = false;
+    {
+      int sup = 0;
+#pragma unroll
+      for (int sl = 0; sl < CPL; ++sl)
+        sup += __popc((__ballot_sync(kFull, sh0[sl].sup) >> t.group_base) & ((1u << G) - 1u));
+      asleep = P.sleep_lin > 0.0f && dot(v, v) < P.sleep_lin * P.sleep_lin && dot(w, w) < P.sleep_ang * P.sleep_ang &&
+               !cc_near && lnear == 0u && near_mask != 0u && sup >= 3;
+    }
+    if (asleep) {
+      v = mk(0, 0, 0); w = mk(0, 0, 0);
+      const float wgt = P.cube_mass[g] * P.gravity * h;   // the support carries the weight
+      if (k0 == P.idx_table && P.report_cube) imp_table.z -= wgt;
+      if (k0 == P.idx_shelf && P.report_cube) imp_shelf.z -= wgt;
+      if (g == 1) imp_cubeb.z += wgt;
+#pragma unroll
+      for (int sl = 0; sl < CPL; ++sl) sh0[sl].hit = false;
+    } else {
+      v.z -= P.gravity * h;   // gravity
+    }
+    // fixed boxes any awake cube of the warp is near (the loops below must be warp-uniform)
+    unsigned near_any = 0u;
+#pragma unroll
+    for (int sl = 0; sl < CPL; ++sl) near_any |= fold<G>(__ballot_sync(kFull, near_c[sl] && !asleep)) << (sl * G);
+    if (asleep) near_mask = 0u;
+    // accumulators of the own corners against box k0: warm start from the previous sub-step of this step
+    unsigned cur_st = 0u, cur_lk = 0u, cur_cc = 0u;
+#pragma unroll
+    for (int sl = 0; sl < CPL; ++sl) {
+      lam_st[sl] = warm_prepare(lam_st[sl], sh0[sl].hit && ((prev_st >> sl) & 1u), sh0[sl].n, 0.5f * (mu_c + P.st[k0].mu), P.warm_start);
+      if (sh0[sl].hit) cur_st |= 1u << sl;
+    }
+    unsigned live = 0xffffffu;  // link contact slots (pair fi, direction/slot phs) not yet known to be empty
 
 #pragma unroll 1
     for (int p = 0; p < c.passes; ++p) {
-      // (a) own cube against the fixed boxes
-#pragma unroll 1
-      for (unsigned todo_k = near_any; todo_k; todo_k &= todo_k - 1) {
-        const int ks = __ffs(todo_k) - 1;
-        const OBox3 sb = obox_of(P.st[ks]);
-        const bool near = (near_mask >> ks) & 1u;
-        const float mu = 0.5f * (mu_c + P.st[ks].mu);
-        V3 got = mk(0, 0, 0);
-#pragma unroll 1
-        for (int sl = 0; sl < CPL; ++sl) {
-          const V3 r = (CPL > 1 && sl > 0) ? ra[CPL - 1] : ra[0];
-          StaticHit sh;
-          if (ks == ks0) sh = (CPL > 1 && sl > 0) ? sh0[CPL - 1] : sh0[0];
-          else sh = static_hit(near, x + r, r, sb, im, ii, inv_h, P);
-          got = got + apply_static_hits<G>(sh, r, t.group_base, v, w, im, ii, mu);
-        }
-        // impulses received by the fixed box = -(impulses on the cube)
-        if (ks == P.idx_table && P.report_cube) imp_table = imp_table - got;
-        if (ks == P.idx_shelf && P.report_cube) imp_shelf = imp_shelf - got;
-        if (g == 1) imp_cubeb = imp_cubeb + got;
-      }
-      // (b) cubeA against cubeB, both ways; every lane of the team applies every impulse to replicas of both cubes
-      if (__any_sync(kFull, cc_near)) {
-        const V3 vo = shfl3(v, t.other), wo = shfl3(w, t.other);
-        Dyn3 A = g == 0 ? dyn_cube(v, w, x, im, ii) : dyn_cube(vo, wo, xo, imo, iio);   // cubeA
-        Dyn3 B = g == 0 ? dyn_cube(vo, wo, xo, imo, iio) : dyn_cube(v, w, x, im, ii);   // cubeB
-        const float mu = 0.5f * (P.cube_mu[0] + P.cube_mu[1]);
-        V3 got = mk(0, 0, 0);
-#pragma unroll 1
-        for (int phs = 0; phs < 2 * CPL; ++phs) {
-          // ph 0: corners of cubeA in cubeB (found by group 0), normal out of cubeB;
-          // ph 1: corners of cubeB in cubeA (found by group 1), normal out of cubeA -> solve with -n
-          const int ph = phs / CPL, sl = phs - ph * CPL;
-          const V3 pc = x + ((CPL > 1 && sl > 0) ? ra[CPL - 1] : ra[0]);
-          V3 n = mk(0, 0, 0);
-          float depth = 0.0f;
-          const bool hit = cc_near && g == ph && point_in_box(pc, ob, P.contact_margin, n, depth);
-          const float sg = ph == 0 ? 1.0f : -1.0f;
-          got = got + apply_hits<G>(hit, n, depth, pc, t.team_base + G * ph, cc_near, [&](V3 nj, float dj, V3 pj) {
-            return solve_contact3_call(A, B, sg * nj, dj, pj, mu, h, P);
-          });
-        }
-        if (cc_near) {
-          v = g == 0 ? A.v : B.v;
-          w = g == 0 ? A.w : B.w;
-          if (g == 1) imp_cubeb = imp_cubeb - got;  // cubeB received -(impulse on cubeA)
-        }
-      }
-      // (c) links against the cubes in the order (f, cubeA), (f, cubeB); pair (f, i) is worked by group i.
+      // (a) links against the cubes in the order (f, cubeA), (f, cubeB); pair (f, i) is worked by group i.
       // P.link_sweeps sweeps: the finger - cube - finger chain of a grasp only settles after a few sweeps over its
       // own contacts. `live` remembers which (pair, direction, slot) found no contact at all in this sub-step
       // (positions are fixed), so later sweeps and passes skip their detection.
       if (__any_sync(kFull, lnear != 0u)) {
 #pragma unroll 1
         for (int sw = 0; sw < P.link_sweeps; ++sw) {
+          const bool first = p == 0 && sw == 0;
 #pragma unroll 1
           for (int fi = 0; fi < 6; ++fi) {
             const int f = fi >> 1, i = fi & 1;
@@ -632,7 +691,16 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
               if (!hb) { live &= ~(1u << (4 * fi + phs)); continue; }
               const float sg = ph == 0 ? 1.0f : -1.0f;
               const LinkHit lh = link_hit(hit, sg * n, depth, pt, H.v, H.w, H.p, axis, ims, x, im, ii, inv_h, P);
-              got = got + apply_link_hits<G>(lh, hb, t.team_base + G * i, mine, axis, sl_f, ims, v, w, im, ii, mu);
+              // accumulator of this lane's slot (f, direction, corner slot) of the own cube, in shared memory
+              const int slot = f * (2 * CPL) + phs;
+              float4* Ls = slam + slot * blockDim.x;
+              float4 Lv = *Ls;
+              if (first) {
+                Lv = warm_prepare(Lv, hit && ((prev_lk >> slot) & 1u), lh.n, mu, P.warm_start);
+                if (hit) cur_lk |= 1u << slot;
+              }
+              got = got + apply_link_hits<G>(lh, hb, t.team_base + G * i, mine, axis, sl_f, ims, v, w, im, ii, mu, Lv, first);
+              if (hit) *Ls = Lv;
             }
             if (mine && i == 1) imp_cubeb = imp_cubeb - got;
             // the finger's sliding speed is shared by both groups: take it from the group that worked the pair
@@ -643,7 +711,68 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
           }
         }
       }
+      // (b) cubeA against cubeB, both ways; every lane of the team applies every impulse to replicas of both cubes
+      if (__any_sync(kFull, cc_near)) {
+        const V3 vo = shfl3(v, t.other), wo = shfl3(w, t.other);
+        Dyn3 A = g == 0 ? dyn_cube(v, w, x, im, ii) : dyn_cube(vo, wo, xo, imo, iio);   // cubeA
+        Dyn3 B = g == 0 ? dyn_cube(vo, wo, xo, imo, iio) : dyn_cube(v, w, x, im, ii);   // cubeB
+        const float mu = 0.5f * (P.cube_mu[0] + P.cube_mu[1]);
+        V3 got = mk(0, 0, 0);
+#pragma unroll 1
+        for (int phs = 0; phs < 2 * CPL; ++phs) {
+          // ph 0: corners of cubeA in cubeB (found by group 0), normal out of cubeB;
+          // ph 1: corners of cubeB in cubeA (found by group 1), normal out of cubeA -> solve with -n
+          const int ph = phs / CPL, sl = phs - ph * CPL;
+          const V3 pc = x + ((CPL > 1 && sl > 0) ? ra[CPL - 1] : ra[0]);
+          V3 n = mk(0, 0, 0);
+          float depth = 0.0f;
+          const bool hit = cc_near && g == ph && point_in_box(pc, ob, P.contact_margin, n, depth);
+          const float sg = ph == 0 ? 1.0f : -1.0f;
+          // accumulator of the own corner slot against the other cube (the group that finds the contact owns it)
+          float4* Ls = slam + (6 * CPL + sl) * blockDim.x;
+          float4 Lv = *Ls;
+          if (p == 0) {
+            Lv = warm_prepare(Lv, hit && ((prev_cc >> sl) & 1u), sg * n, mu, P.warm_start);
+            if (hit) cur_cc |= 1u << sl;
+          }
+          got = got + apply_hits<G>(hit, n, depth, pc, Lv, t.team_base + G * ph, cc_near, [&](V3 nj, float dj, V3 pj, float4& Lj) {
+            return solve_contact3_call(A, B, sg * nj, dj, pj, mu, h, P, Lj, p == 0);
+          });
+          if (hit) *Ls = Lv;
+        }
+        if (cc_near) {
+          v = g == 0 ? A.v : B.v;
+          w = g == 0 ? A.w : B.w;
+          if (g == 1) imp_cubeb = imp_cubeb - got;  // cubeB received -(impulse on cubeA)
+        }
+      }
+      // (c) own cube against the fixed boxes, LAST in the pass: what a kinematic link pushes into the table is pushed
+      // back out by the table in the same pass
+#pragma unroll 1
+      for (unsigned todo_k = near_any; todo_k; todo_k &= todo_k - 1) {
+        const int ks = __ffs(todo_k) - 1;
+        const OBox3 sb = obox_of(P.st[ks]);
+        const bool near = (near_mask >> ks) & 1u;
+        const bool keep = near && ks == k0;
+        const float mu = 0.5f * (mu_c + P.st[ks].mu);
+        V3 got = mk(0, 0, 0);
+#pragma unroll 1
+        for (int sl = 0; sl < CPL; ++sl) {
+          const V3 r = (CPL > 1 && sl > 0) ? ra[CPL - 1] : ra[0];
+          StaticHit sh;
+          if (keep) sh = (CPL > 1 && sl > 0) ? sh0[CPL - 1] : sh0[0];
+          else sh = static_hit(near, x + r, r, sb, im, ii, inv_h, P);
+          float4 Lr = (CPL > 1 && sl > 0) ? lam_st[CPL - 1] : lam_st[0];
+          got = got + apply_static_hits<G>(sh, r, t.group_base, v, w, im, ii, mu, Lr, keep, p == 0);
+          if (CPL > 1 && sl > 0) lam_st[CPL - 1] = Lr; else lam_st[0] = Lr;
+        }
+        // impulses received by the fixed box = -(impulses on the cube)
+        if (ks == P.idx_table && P.report_cube) imp_table = imp_table - got;
+        if (ks == P.idx_shelf && P.report_cube) imp_shelf = imp_shelf - got;
+        if (g == 1) imp_cubeb = imp_cubeb + got;
+      }
     }
+    prev_st = cur_st; prev_lk = cur_lk; prev_cc = cur_cc;
     e.cu.v = v; e.cu.w = w;
 #pragma unroll
     for (int f = 0; f < 2; ++f) {
@@ -684,7 +813,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
         }
       }
     }
-    // ---- 4. positions
+    // ---- 5. positions
 #pragma unroll
     for (int j = 7; j < 9; ++j) {   // the arm joints were integrated by the run-ahead
       float qn = e.q[j] + h * e.qd[j];
@@ -692,7 +821,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       if (qn > P.q_upper[j]) { qn = P.q_upper[j]; e.qd[j] = 0.0f; }
       e.q[j] = qn;
     }
-    {
+    if (!asleep) {
       Cube& cu = e.cu;
       cu.p = cu.p + h * cu.v;
       const float qx = cu.qx, qy = cu.qy, qz = cu.qz, qw = cu.qw, hh = 0.5f * h;
@@ -734,6 +863,25 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       }
     }
   }
+}
+
+// Body of k_rollout_team: which sample (or producer row) this thread's team works on.
+template <int CPL>
+DEV void team_kernel_body(const RolloutCfg& c, const PandaParams& P, const RolloutBufs& b) {
+  constexpr int TM = TeamShape<CPL>::kTeam;
+  const TeamLane t = team_lane<CPL>();
+  const bool use_refs = b.refs != nullptr;
+  const bool producer = use_refs && blockIdx.x == 0;
+  const int which = t.lane / TM;   // producer CTA: team 0 replays global row 0, team 1 global row Kg/2
+  const int kraw = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x + threadIdx.x) / TM;
+  const bool valid = !producer && kraw < c.K;
+  int k = kraw < c.K ? kraw : c.K - 1;   // idle teams shadow the last sample so that every shuffle has 32 lanes
+  int kg = c.offset + k;
+  if (producer) {
+    kg = (which == 1 && c.multi_modal) ? c.Kg / 2 : 0;
+    k = (kg >= c.offset && kg < c.offset + c.K) ? kg - c.offset : -1;
+  }
+  team_rollout<CPL>(c, P, b, t, k, kg, valid, producer, which);
 }
 
 }  // namespace m3

@@ -65,6 +65,7 @@ class PandaScene(C.Structure):
         ("drive_damping", f32), ("arm_inertia", f32), ("finger_mass", f32), ("robot_mu", f32),
         ("finger_half", f32 * 3), ("finger_center", f32 * 3), ("hand_half", f32 * 3), ("hand_center", f32 * 3),
         ("contact_margin", f32), ("baumgarte", f32), ("slop", f32), ("max_corr_vel", f32), ("penalty_stiffness", f32),
+        ("joint_inertia", f32 * MAX_NU), ("warm_start", f32), ("sleep_lin", f32), ("sleep_ang", f32), ("sleep_gap", f32),
         ("n_static", i32), ("n_actors", i32), ("idx_table", i32), ("idx_shelf", i32), ("link_sweeps", i32), ("report_cube_contacts", i32),
         ("cube_a", Body), ("cube_b", Body), ("statics", Box * MAX_STATIC),
     ]

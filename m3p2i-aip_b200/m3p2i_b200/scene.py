@@ -227,7 +227,12 @@ def build_panda_scene(actors=None):
     s.slop = 0.0005
     s.max_corr_vel = 0.5
     s.penalty_stiffness = 2000.0
-    s.link_sweeps = 4
+    # link masses from the collision meshes at IsaacGym's default density, reflected onto the joint axes at the
+    # initial pose (tools/panda_inertia.py); the fingers keep finger_mass
+    _fill(s.joint_inertia, [1.3195, 2.1231, 1.2994, 0.9183, 0.0271, 0.0366, 0.0030, 0.0, 0.0])
+    s.warm_start = 0.9
+    s.sleep_lin, s.sleep_ang, s.sleep_gap = 5e-3, 5e-2, 2e-3
+    s.link_sweeps = 2
     s.report_cube_contacts = 0
     s.n_actors = len(actors)
     s.idx_table = -1

@@ -34,6 +34,15 @@ typedef struct {
   float p[3], q[4], v[3], w[3]; /* position, quaternion xyzw, linear, angular velocity */
 } OCube;
 
+/* accumulated impulse of one contact slot: normal magnitude and tangential (world) vector; `stamp` = 1-based index of
+ * the last sub-step (of the current step) in which the slot held a contact; `fresh` = a warm-start impulse is pending */
+typedef struct { float n, t[3]; int stamp, fresh; } OLam;
+typedef struct {
+  OLam st[2][8];        /* cube i against its first near fixed box, corner */
+  OLam cc[2][8];        /* 0: corners of cubeA in cubeB, 1: corners of cubeB in cubeA */
+  OLam lk[3][2][2][8];  /* link f, cube i, 0: link corners in the cube / 1: cube corners in the link */
+} OCache;
+
 typedef struct {
   float q[9], qd[9];
   OCube cube[2];      /* 0 = cubeA, 1 = cubeB */
@@ -347,6 +356,112 @@ static inline void o_panda_init(OPandaEnv* e, const M3P2IPandaScene* sc, const f
   }
 }
 
+/* One detected contact of a sub-step. Positions are fixed inside a sub-step, so detection runs once; the passes
+ * then visit the records in the fixed solve order. */
+typedef struct {
+  OSolv3 *A, *B;
+  float n[3], depth, p[3], mu;
+  OLam* L;       /* accumulator slot, or NULL: plain (non-accumulated) solve */
+} OContact;
+
+/* Accumulated-impulse form of o_solve_contact3: the normal impulse is clamped on its running total (a later visit may
+ * take back what an earlier one over-applied), the friction impulse is a tangential vector clamped to the Coulomb
+ * cone of the TOTAL normal impulse. A slot that was in contact in the previous sub-step of the same step() first
+ * re-applies `warm_start` times what it held then (o_detect prepared it; applied here, at the slot's first visit). */
+static inline void o_solve_contact3_acc(const OContact* c, float h, const M3P2IPandaScene* sc) {
+  OSolv3 *A = c->A, *B = c->B;
+  OLam* L = c->L;
+  const float* n = c->n;
+  float ra[3], rb[3], va[3], vb[3], rv[3];
+  for (int i = 0; i < 3; ++i) { ra[i] = c->p[i] - A->x[i]; rb[i] = c->p[i] - B->x[i]; }
+  if (L->fresh) {
+    float P[3] = {L->n * n[0] + L->t[0], L->n * n[1] + L->t[1], L->n * n[2] + L->t[2]};
+    o_apply_impulse(A, ra, P, 1.0f); o_apply_impulse(B, rb, P, -1.0f);
+    L->fresh = 0;
+  }
+  o_point_vel(A, ra, va); o_point_vel(B, rb, vb);
+  for (int i = 0; i < 3; ++i) rv[i] = va[i] - vb[i];
+  float vn = q_dot3(rv, n);
+  float kn = o_eff_mass(A, ra, n) + o_eff_mass(B, rb, n);
+  if (kn <= 0.0f) return;
+  float target;
+  if (c->depth > 0.0f) {
+    float pen = c->depth - sc->slop;
+    if (pen < 0.0f) pen = 0.0f;
+    target = sc->baumgarte * pen / h;
+    if (target > sc->max_corr_vel) target = sc->max_corr_vel;
+  } else {
+    target = c->depth / h;
+  }
+  float ln = L->n + (target - vn) / kn;
+  if (ln < 0.0f) ln = 0.0f;
+  float dj = ln - L->n;
+  L->n = ln;
+  float P[3] = {dj * n[0], dj * n[1], dj * n[2]};
+  o_apply_impulse(A, ra, P, 1.0f); o_apply_impulse(B, rb, P, -1.0f);
+  o_point_vel(A, ra, va); o_point_vel(B, rb, vb);
+  for (int i = 0; i < 3; ++i) rv[i] = va[i] - vb[i];
+  vn = q_dot3(rv, n);
+  float t[3] = {rv[0] - vn * n[0], rv[1] - vn * n[1], rv[2] - vn * n[2]};
+  float vt2 = q_dot3(t, t);
+  float lt[3] = {L->t[0], L->t[1], L->t[2]};
+  if (vt2 >= 1e-18f) {
+    float vt = sqrtf(vt2);
+    for (int i = 0; i < 3; ++i) t[i] /= vt;
+    float kt = o_eff_mass(A, ra, t) + o_eff_mass(B, rb, t);
+    if (kt > 0.0f) { float jt = vt / kt; for (int i = 0; i < 3; ++i) lt[i] -= jt * t[i]; }
+  }
+  float lim = c->mu * ln, m2 = q_dot3(lt, lt);
+  if (m2 > lim * lim) { float k_ = lim / sqrtf(m2); for (int i = 0; i < 3; ++i) lt[i] *= k_; }
+  float Pt[3] = {lt[0] - L->t[0], lt[1] - L->t[1], lt[2] - L->t[2]};
+  for (int i = 0; i < 3; ++i) L->t[i] = lt[i];
+  o_apply_impulse(A, ra, Pt, 1.0f); o_apply_impulse(B, rb, Pt, -1.0f);
+}
+
+static inline void o_solve_one(const OContact* c, float h, const M3P2IPandaScene* sc) {
+  if (c->L) { o_solve_contact3_acc(c, h, sc); return; }
+  /* no slot: every visit starts from zero, which is the plain one-shot solve */
+  OLam zero;
+  memset(&zero, 0, sizeof(zero));
+  OContact tmp = *c;
+  tmp.L = &zero;
+  o_solve_contact3_acc(&tmp, h, sc);
+}
+
+/* corners of box `ba` (body A) against `bb` (body B) -> contact records (normal from B to A; flip: the records are for
+ * the pair (B, A) with the normal reversed, as o_corners_vs_box3). `slots` = the 8 accumulators of this corner set or
+ * NULL; `sub` = 1-based sub-step index inside the current step(). Returns the new count. */
+static inline int o_detect(OContact* out, int cnt, OSolv3* A, const OBox3* ba, OSolv3* B, const OBox3* bb, float mu,
+                           const M3P2IPandaScene* sc, int flip, OLam* slots, int sub) {
+  for (int i = 0; i < 8; ++i) {
+    float p[3], n[3], depth;
+    o_box_corner(ba, i, p);
+    if (!o_point_in_box(p, bb, sc->contact_margin, n, &depth)) continue;
+    OContact* c = &out[cnt++];
+    if (!flip) { c->A = A; c->B = B; memcpy(c->n, n, 12); }
+    else { c->A = B; c->B = A; c->n[0] = -n[0]; c->n[1] = -n[1]; c->n[2] = -n[2]; }
+    c->depth = depth; memcpy(c->p, p, 12); c->mu = mu; c->L = slots ? &slots[i] : NULL;
+    if (!slots) continue;
+    OLam* L = &slots[i];
+    if (L->stamp == sub - 1 && sub > 1) {
+      /* warm start: what the slot held, scaled, in the tangent plane of the new normal, inside the new cone */
+      const float* m = c->n;
+      float tn = q_dot3(L->t, m);
+      float ln = sc->warm_start * L->n;
+      float lt[3];
+      for (int r = 0; r < 3; ++r) lt[r] = sc->warm_start * (L->t[r] - tn * m[r]);
+      float lim = mu * ln, m2 = q_dot3(lt, lt);
+      if (m2 > lim * lim) { float k_ = lim / sqrtf(m2); for (int r = 0; r < 3; ++r) lt[r] *= k_; }
+      L->n = ln; L->t[0] = lt[0]; L->t[1] = lt[1]; L->t[2] = lt[2];
+      L->fresh = 1;
+    } else {
+      L->n = 0.0f; L->t[0] = L->t[1] = L->t[2] = 0.0f; L->fresh = 0;
+    }
+    L->stamp = sub;
+  }
+  return cnt;
+}
+
 static inline void o_panda_step(OPandaEnv* e, const M3P2IPandaScene* sc, const M3P2IConfig* cfg, const float* u) {
   const int ns = cfg->substeps;
   const float h = cfg->dt / (float)ns;
@@ -354,10 +469,13 @@ static inline void o_panda_step(OPandaEnv* e, const M3P2IPandaScene* sc, const M
   const M3P2IBody* bp[2] = {&sc->cube_a, &sc->cube_b};
   float imp_table[3] = {0, 0, 0}, imp_shelf[3] = {0, 0, 0}, imp_cubeb[3] = {0, 0, 0};
   float pen_table[3] = {0, 0, 0}, pen_shelf[3] = {0, 0, 0};
+  /* every step() starts cold: accumulated impulses are carried from one sub-step to the next, not across steps */
+  OCache cache;
+  memset(&cache, 0, sizeof(cache));
   for (int s = 0; s < ns; ++s) {
     /* 1. joint drives */
     for (int j = 0; j < 9; ++j) {
-      float m = j < 7 ? sc->arm_inertia : sc->finger_mass;
+      float m = j < 7 ? (sc->joint_inertia[j] > 0.0f ? sc->joint_inertia[j] : sc->arm_inertia) : sc->finger_mass;
       float v = e->qd[j];
       float vs = (m * v + h * D * u[j]) / (m + h * D);
       float f = D * (u[j] - vs);
@@ -369,9 +487,7 @@ static inline void o_panda_step(OPandaEnv* e, const M3P2IPandaScene* sc, const M
       if (e->q[j] >= sc->q_upper[j] && vs > 0.0f) vs = 0.0f;
       e->qd[j] = vs;
     }
-    /* 2. gravity on the cubes */
-    for (int i = 0; i < 2; ++i) e->cube[i].v[2] -= sc->gravity * h;
-    /* 3. contacts */
+    /* link and cube boxes of this sub-step (positions are fixed until step 5) */
     OHand H;
     o_panda_hand(sc, e->q, e->qd, &H);
     OBox3 lbox[3]; /* left finger, right finger, hand */
@@ -403,38 +519,86 @@ static inline void o_panda_step(OPandaEnv* e, const M3P2IPandaScene* sc, const M
       memcpy(C[i].x, e->cube[i].p, 12);
     }
     C[1].acc = imp_cubeb;
+    OSolv3 S[M3P2I_MAX_STATIC];
+    OBox3 sbox[M3P2I_MAX_STATIC];
+    for (int k = 0; k < sc->n_static; ++k) {
+      sbox[k] = o_static_box3(&sc->statics[k]);
+      memset(&S[k], 0, sizeof(OSolv3));
+      memcpy(S[k].x, sbox[k].c, 12);
+      if (k == sc->idx_table && sc->report_cube_contacts) S[k].acc = imp_table;
+      if (k == sc->idx_shelf && sc->report_cube_contacts) S[k].acc = imp_shelf;
+    }
+    const int cc_near = o_boxes_near(&cbox[0], &cbox[1], sc->contact_margin);
+    int lnear[3][2], first_box[2] = {-1, -1};
+    for (int i = 0; i < 2; ++i) {
+      for (int f = 0; f < 3; ++f) lnear[f][i] = o_boxes_near(&lbox[f], &cbox[i], sc->contact_margin);
+      for (int k = 0; k < sc->n_static && first_box[i] < 0; ++k)
+        if (o_boxes_near(&cbox[i], &sbox[k], sc->contact_margin)) first_box[i] = k;
+    }
+    /* 2. sleeping: a cube that is (almost) motionless, rests on its first near fixed box with at least three corners
+     * and has no link and no other cube within the contact margin is neither moved nor solved in this sub-step */
+    int asleep[2] = {0, 0};
+    for (int i = 0; i < 2 && sc->sleep_lin > 0.0f; ++i) {
+      const OCube* c = &e->cube[i];
+      if (!(q_dot3(c->v, c->v) < sc->sleep_lin * sc->sleep_lin && q_dot3(c->w, c->w) < sc->sleep_ang * sc->sleep_ang)) continue;
+      if (cc_near || lnear[0][i] || lnear[1][i] || lnear[2][i] || first_box[i] < 0) continue;
+      int cnt = 0;
+      for (int cI = 0; cI < 8; ++cI) {
+        float p[3], n[3], depth;
+        o_box_corner(&cbox[i], cI, p);
+        if (o_point_in_box(p, &sbox[first_box[i]], sc->contact_margin, n, &depth) && depth > -sc->sleep_gap) ++cnt;
+      }
+      if (cnt < 3) continue;
+      asleep[i] = 1;
+      for (int r = 0; r < 3; ++r) { e->cube[i].v[r] = 0.0f; e->cube[i].w[r] = 0.0f; }
+      /* the support carries the weight */
+      float wgt = bp[i]->mass * sc->gravity * h;
+      if (S[first_box[i]].acc) S[first_box[i]].acc[2] -= wgt;
+      if (i == 1) imp_cubeb[2] += wgt;
+    }
+    /* 3. gravity on the cubes */
+    for (int i = 0; i < 2; ++i) if (!asleep[i]) e->cube[i].v[2] -= sc->gravity * h;
+    /* 4. contacts: detection once per sub-step, in solve order. Accumulators: link/cube and cube/cube contacts, and the
+     * contacts of a cube with its FIRST near fixed box (its support); further fixed boxes use the plain solve. */
+    OContact lk[3 * 2 * 16], ccl[16], st[2 * M3P2I_MAX_STATIC * 8];
+    int n_lk = 0, n_cc = 0, n_st = 0;
+    for (int f = 0; f < 3; ++f)
+      for (int i = 0; i < 2; ++i) {
+        if (asleep[i] || !lnear[f][i]) continue;
+        float mu = 0.5f * (sc->robot_mu + bp[i]->mu);
+        n_lk = o_detect(lk, n_lk, &L[f], &lbox[f], &C[i], &cbox[i], mu, sc, 0, cache.lk[f][i][0], s + 1);
+        n_lk = o_detect(lk, n_lk, &C[i], &cbox[i], &L[f], &lbox[f], mu, sc, 1, cache.lk[f][i][1], s + 1);
+      }
+    if (cc_near) {
+      float mu = 0.5f * (bp[0]->mu + bp[1]->mu);
+      n_cc = o_detect(ccl, n_cc, &C[0], &cbox[0], &C[1], &cbox[1], mu, sc, 0, cache.cc[0], s + 1);
+      n_cc = o_detect(ccl, n_cc, &C[1], &cbox[1], &C[0], &cbox[0], mu, sc, 1, cache.cc[1], s + 1);
+    }
+    for (int i = 0; i < 2; ++i)
+      for (int k = 0; k < sc->n_static; ++k) {
+        if (asleep[i] || !o_boxes_near(&cbox[i], &sbox[k], sc->contact_margin)) continue;
+        n_st = o_detect(st, n_st, &C[i], &cbox[i], &S[k], &sbox[k], 0.5f * (bp[i]->mu + sc->statics[k].mu), sc, 0,
+                        k == first_box[i] ? cache.st[i] : NULL, s + 1);
+      }
+    const int sweeps = sc->link_sweeps > 0 ? sc->link_sweeps : 2;
     for (int p = 0; p < cfg->solver_passes; ++p) {
-      for (int i = 0; i < 2; ++i)
-        for (int k = 0; k < sc->n_static; ++k) {
-          OBox3 sb = o_static_box3(&sc->statics[k]);
-          OSolv3 S;
-          memset(&S, 0, sizeof(S));
-          memcpy(S.x, sb.c, 12);
-          if (k == sc->idx_table && sc->report_cube_contacts) S.acc = imp_table;
-          if (k == sc->idx_shelf && sc->report_cube_contacts) S.acc = imp_shelf;
-          o_box_vs_box3(&C[i], &cbox[i], &S, &sb, 0.5f * (bp[i]->mu + sc->statics[k].mu), h, sc, 0);
-        }
-      o_box_vs_box3(&C[0], &cbox[0], &C[1], &cbox[1], 0.5f * (bp[0]->mu + bp[1]->mu), h, sc, 1);
-      /* the finger - cube - finger chain of a grasp settles only after a few sweeps over its own contacts */
-      for (int sw = 0; sw < (sc->link_sweeps > 0 ? sc->link_sweeps : 4); ++sw)
-        for (int f = 0; f < 3; ++f)
-          for (int i = 0; i < 2; ++i)
-            o_box_vs_box3(&L[f], &lbox[f], &C[i], &cbox[i], 0.5f * (sc->robot_mu + bp[i]->mu), h, sc, 1);
+      /* links (a few sweeps: the finger - cube - finger chain of a grasp) and cube/cube first, the fixed boxes LAST:
+       * what a kinematic link pushes into the table is pushed back out by the table in the same pass */
+      for (int sw = 0; sw < sweeps; ++sw)
+        for (int j = 0; j < n_lk; ++j) o_solve_one(&lk[j], h, sc);
+      for (int j = 0; j < n_cc; ++j) o_solve_one(&ccl[j], h, sc);
+      for (int j = 0; j < n_st; ++j) o_solve_one(&st[j], h, sc);
     }
     /* finger speed limit also holds after contacts */
     for (int j = 7; j < 9; ++j) e->qd[j] = q_clamp(e->qd[j], -sc->qd_limit[j], sc->qd_limit[j]);
     /* kinematic links against the static bodies named by the collision cost */
     for (int f = 0; f < 3; ++f) {
-      if (sc->idx_table >= 0) {
-        OBox3 sb = o_static_box3(&sc->statics[sc->idx_table]);
-        o_link_vs_static(&lbox[f], &L[f], &sb, 0.5f * (sc->robot_mu + sc->statics[sc->idx_table].mu), sc, pen_table);
-      }
-      if (sc->idx_shelf >= 0) {
-        OBox3 sb = o_static_box3(&sc->statics[sc->idx_shelf]);
-        o_link_vs_static(&lbox[f], &L[f], &sb, 0.5f * (sc->robot_mu + sc->statics[sc->idx_shelf].mu), sc, pen_shelf);
-      }
+      if (sc->idx_table >= 0)
+        o_link_vs_static(&lbox[f], &L[f], &sbox[sc->idx_table], 0.5f * (sc->robot_mu + sc->statics[sc->idx_table].mu), sc, pen_table);
+      if (sc->idx_shelf >= 0)
+        o_link_vs_static(&lbox[f], &L[f], &sbox[sc->idx_shelf], 0.5f * (sc->robot_mu + sc->statics[sc->idx_shelf].mu), sc, pen_shelf);
     }
-    /* 4. positions */
+    /* 5. positions */
     for (int j = 0; j < 9; ++j) {
       float qn = e->q[j] + h * e->qd[j];
       if (qn < sc->q_lower[j]) { qn = sc->q_lower[j]; e->qd[j] = 0.0f; }
@@ -442,6 +606,7 @@ static inline void o_panda_step(OPandaEnv* e, const M3P2IPandaScene* sc, const M
       e->q[j] = qn;
     }
     for (int i = 0; i < 2; ++i) {
+      if (asleep[i]) continue;
       OCube* c = &e->cube[i];
       for (int r = 0; r < 3; ++r) c->p[r] += h * c->v[r];
       /* q <- normalize(q + h/2 * (w,0) (x) q), xyzw */

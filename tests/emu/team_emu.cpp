@@ -1,0 +1,186 @@
+// team_emu.cpp -- runs the lane-cooperative Panda rollout (m3p2i-aip_b200/csrc/panda_team.cuh, the body of
+// k_rollout_team) on the host, 32 fibers per warp in lock step (cuda_emu.h). TEST INFRASTRUCTURE ONLY: it lets the
+// CPU test tier compare the kernel's device code with the oracle without a GPU. Built by tests/emu/build.py.
+#include "cuda_emu.h"
+
+#include <vector>
+
+#include "../../m3p2i-aip_b200/csrc/params_host.h"
+#include "../../m3p2i-aip_b200/csrc/panda_team.cuh"
+
+namespace emu { Warp* W = nullptr; }
+using namespace m3;
+
+namespace {
+struct Launch {
+  const RolloutCfg* c;
+  const PandaParams* P;
+  const RolloutBufs* b;
+  int cpl;
+};
+Launch g_launch;
+
+void lane_main() {
+  if (g_launch.cpl == 1) team_kernel_body<1>(*g_launch.c, *g_launch.P, *g_launch.b);
+  else team_kernel_body<2>(*g_launch.c, *g_launch.P, *g_launch.b);
+  emu::me().done = true;
+  swapcontext(&emu::me().ctx, &emu::W->sched);
+}
+
+constexpr size_t kStack = 1 << 20;
+
+long run_warp(emu::Warp& w, unsigned block, unsigned block_dim, unsigned warp_in_block, void* smem) {
+  emu::W = &w;
+  w.bid = {block, 0, 0}; w.bdim = {block_dim, 1, 1}; w.smem = smem; w.collectives = 0;
+  for (int l = 0; l < 32; ++l) {
+    emu::Lane& L = w.lane[l];
+    L.done = false; L.n_coll = 0; L.tid = {warp_in_block * 32 + (unsigned)l, 0, 0};
+    getcontext(&L.ctx);
+    L.ctx.uc_stack.ss_sp = L.stack; L.ctx.uc_stack.ss_size = kStack; L.ctx.uc_link = &w.sched;
+    makecontext(&L.ctx, lane_main, 0);
+  }
+  for (;;) {
+    int done = 0;
+    for (int l = 0; l < 32; ++l) {
+      if (w.lane[l].done) { ++done; continue; }
+      w.cur = l;
+      swapcontext(&w.sched, &w.lane[l].ctx);
+      if (w.lane[l].done) ++done;
+    }
+    if (done == 32) break;
+    if (done != 0) {
+      // some lanes returned while others wait at a collective: they would hang on the GPU
+      bool all = true;
+      for (int l = 0; l < 32; ++l) all = all && w.lane[l].done;
+      if (!all) {
+        int waiting = 0;
+        for (int l = 0; l < 32; ++l) waiting += !w.lane[l].done;
+        if (waiting != 32 && done != 32) { fprintf(stderr, "emu: %d lanes exited while %d wait at a collective\n", done, waiting); abort(); }
+      }
+    }
+  }
+  return w.collectives;
+}
+}  // namespace
+
+extern "C" {
+
+// Open-loop rollout of caller-supplied actions [K,T,nu] from one broadcast state, exactly what
+// m3p2i_rollout_actions launches for panda_env with `lanes` (8 or 16) lanes per sample.
+// Outputs (any may be NULL): states [K,T,4], cost_h [K,T], env_end [K,53], collectives (warp collectives executed).
+int emu_team_rollout_actions(const M3P2IConfig* cfg, const M3P2IPandaScene* scene, int task, const float* goal,
+                             int gripper, const float* dof, const float* root, const float* actions, int lanes,
+                             int block_threads, float* out_states, float* out_cost_h, float* out_env_end,
+                             long* out_collectives) {
+  if (!cfg || !scene || !actions || (lanes != 8 && lanes != 16) || block_threads % 32 || block_threads < 32) return -1;
+  const int K = cfg->num_samples, T = cfg->horizon, NU = 9, nf = kPandaEnvFloats;
+  PandaParams P;
+  memset(&P, 0, sizeof(P));
+  M3P2IPandaScene sc = *scene;
+  for (int k = 0; k < sc.n_static; ++k) {   // movable statics follow the real state (m3p2i_set_state)
+    M3P2IBox& bx = sc.statics[k];
+    if (bx.actor >= 0 && bx.actor < sc.n_actors) { memcpy(bx.pos, root + 13 * bx.actor, 12); memcpy(bx.quat, root + 13 * bx.actor + 3, 16); }
+  }
+  build_panda_params(sc, P);
+  RolloutCfg c;
+  memset(&c, 0, sizeof(c));
+  c.K = K; c.T = T; c.nu = NU; c.Kg = cfg->num_samples_global > 0 ? cfg->num_samples_global : K; c.offset = cfg->sample_offset;
+  c.multi_modal = cfg->multi_modal; c.null_action = cfg->sample_null_action; c.noise_mode = M3P2I_NOISE_TABLE;
+  c.substeps = cfg->substeps > 0 ? cfg->substeps : 2; c.passes = cfg->solver_passes > 0 ? cfg->solver_passes : 2;
+  c.task = task; c.gripper = gripper; c.env_live = 0; c.store_env = 1; c.open_loop = 1; c.align = 0; c.lanes = lanes;
+  c.dt = cfg->dt; c.gamma = cfg->gamma; c.u_scale = cfg->u_scale; c.kp_suction = cfg->kp_suction;
+  c.pre_height_diff = cfg->pre_height_diff; c.tilt_cos = cfg->tilt_cos_theta;
+  memcpy(c.u_min, cfg->u_min, sizeof(c.u_min)); memcpy(c.u_max, cfg->u_max, sizeof(c.u_max)); memcpy(c.sigma, cfg->sigma, sizeof(c.sigma));
+  if (goal) memcpy(c.goal, goal, sizeof(float) * 7);
+  const bool refs = task == M3P2I_TASK_REACH;
+  c.epoch = 64;
+
+  std::vector<float> base(64, 0.0f), env((size_t)nf * K, 0.0f), vel((size_t)NU * K), act_in((size_t)T * NU * K), act((size_t)T * NU * K),
+      cost_h((size_t)T * K), J(K), cost_sum(K), seq((size_t)SEQ_COUNT * T * NU, 0.0f);
+  std::vector<float4> states((size_t)T * K);
+  std::vector<PandaRef> ref_buf(T);
+  unsigned flags[16] = {0};
+  for (int j = 0; j < 18; ++j) base[j] = dof[j];
+  memcpy(base.data() + 18, root + 13 * sc.cube_a.actor, sizeof(float) * 13);
+  memcpy(base.data() + 31, root + 13 * sc.cube_b.actor, sizeof(float) * 13);
+  for (int k = 0; k < K; ++k)
+    for (int j = 0; j < T * NU; ++j) act_in[(size_t)j * K + k] = actions[(size_t)k * T * NU + j];
+  RolloutBufs b;
+  memset(&b, 0, sizeof(b));
+  b.seq = seq.data(); b.actions_in = act_in.data(); b.base = base.data(); b.env = env.data(); b.vel_target = vel.data();
+  b.actions = act.data(); b.states = states.data(); b.cost_h = cost_h.data(); b.J = J.data(); b.cost_sum = cost_sum.data();
+  b.refs = refs ? ref_buf.data() : nullptr; b.ref_flags = flags;
+
+  const int cpl = 16 / lanes, teams_per_block = block_threads / lanes, extra = refs ? 1 : 0;
+  const int grid = (K + teams_per_block - 1) / teams_per_block + extra;
+  g_launch = {&c, &P, &b, cpl};
+  emu::Warp* w = new emu::Warp();
+  for (int l = 0; l < 32; ++l) w->lane[l].stack = static_cast<char*>(malloc(kStack));
+  std::vector<float4> smem((size_t)7 * cpl * block_threads);
+  long coll = 0;
+  for (int blk = 0; blk < grid; ++blk)   // CTA 0 (the producer of the reach rows) first, as on the GPU
+    for (int wi = 0; wi < block_threads / 32; ++wi) coll += run_warp(*w, blk, block_threads, wi, smem.data());
+  for (int l = 0; l < 32; ++l) free(w->lane[l].stack);
+  delete w;
+  emu::W = nullptr;
+  if (out_states)
+    for (int k = 0; k < K; ++k)
+      for (int t = 0; t < T; ++t) memcpy(out_states + ((size_t)k * T + t) * 4, &states[(size_t)t * K + k], 16);
+  if (out_cost_h)
+    for (int k = 0; k < K; ++k)
+      for (int t = 0; t < T; ++t) out_cost_h[(size_t)k * T + t] = cost_h[(size_t)t * K + k];
+  if (out_env_end)
+    for (int k = 0; k < K; ++k)
+      for (int f = 0; f < nf; ++f) out_env_end[(size_t)k * nf + f] = env[(size_t)f * K + k];
+  if (out_collectives) *out_collectives = coll;
+  return 0;
+}
+
+// The same open-loop rollout with the thread-per-sample device code (panda_step / panda_cost of panda_env.cuh, the
+// body of k_rollout<panda_env>, k_sim_step and the producer rows). pick / place only (no batch rows are read).
+int emu_thread_rollout_actions(const M3P2IConfig* cfg, const M3P2IPandaScene* scene, int task, const float* goal,
+                               int gripper, const float* dof, const float* root, const float* actions,
+                               float* out_states, float* out_cost_h, float* out_env_end) {
+  if (!cfg || !scene || !actions || task == M3P2I_TASK_REACH) return -1;
+  const int K = cfg->num_samples, T = cfg->horizon, NU = 9, nf = kPandaEnvFloats;
+  PandaParams P;
+  memset(&P, 0, sizeof(P));
+  M3P2IPandaScene sc = *scene;
+  for (int k = 0; k < sc.n_static; ++k) {
+    M3P2IBox& bx = sc.statics[k];
+    if (bx.actor >= 0 && bx.actor < sc.n_actors) { memcpy(bx.pos, root + 13 * bx.actor, 12); memcpy(bx.quat, root + 13 * bx.actor + 3, 16); }
+  }
+  build_panda_params(sc, P);
+  RolloutCfg c;
+  memset(&c, 0, sizeof(c));
+  c.K = K; c.T = T; c.nu = NU; c.Kg = cfg->num_samples_global > 0 ? cfg->num_samples_global : K; c.offset = cfg->sample_offset;
+  c.multi_modal = cfg->multi_modal; c.task = task; c.gripper = gripper;
+  c.substeps = cfg->substeps > 0 ? cfg->substeps : 2; c.passes = cfg->solver_passes > 0 ? cfg->solver_passes : 2;
+  c.dt = cfg->dt; c.gamma = cfg->gamma; c.u_scale = cfg->u_scale; c.pre_height_diff = cfg->pre_height_diff; c.tilt_cos = cfg->tilt_cos_theta;
+  if (goal) memcpy(c.goal, goal, sizeof(float) * 7);
+  std::vector<float> base(64, 0.0f);
+  for (int j = 0; j < 18; ++j) base[j] = dof[j];
+  memcpy(base.data() + 18, root + 13 * sc.cube_a.actor, sizeof(float) * 13);
+  memcpy(base.data() + 31, root + 13 * sc.cube_b.actor, sizeof(float) * 13);
+  std::vector<float> env_out(nf);
+  for (int k = 0; k < K; ++k) {
+    PandaEnv e;
+    e.load(base.data(), 1, 0);
+    for (int t = 0; t < T; ++t) {
+      float u[NU];
+      for (int d = 0; d < NU; ++d) u[d] = c.u_scale * actions[((size_t)k * T + t) * NU + d];
+      if (cfg->sample_null_action && c.offset + k == c.Kg - 1)
+        for (int d = 0; d < NU; ++d) u[d] = 0.0f;
+      panda_step(e, P, u, c.dt, c.substeps, c.passes);
+      PandaRef r;
+      r.cube0[0] = e.cube[0].p.x; r.cube0[1] = e.cube[0].p.y; r.cube0[2] = e.cube[0].p.z; r.sel_axis = sel_axis_of(e.cube[0]);
+      const float cost = panda_cost(e, P, c, c.offset + k, r);
+      if (out_cost_h) out_cost_h[(size_t)k * T + t] = cost;
+      if (out_states) { const float4 row = e.state_row(); memcpy(out_states + ((size_t)k * T + t) * 4, &row, 16); }
+    }
+    if (out_env_end) { e.store(env_out.data(), 1, 0); memcpy(out_env_end + (size_t)k * nf, env_out.data(), sizeof(float) * nf); }
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -233,9 +233,7 @@ def test_reactive_pick_cpu():
 
 @pytest.mark.gpu
 def test_reactive_pick_gpu():
-    """Same episode on the CUDA path. Closed loops amplify rounding, so the trajectory differs from the oracle's: here
-    the gripper grasps cubeA, lifts it and carries it 0.4 m to within a few cm of the pre-place pose (measured: 0.045 m
-    at tick 360, hovering 5-10 cm off afterwards without hitting the 3 cm switching threshold); the test asserts the
-    carry, the CPU variant asserts the completed task."""
-    task, dist, n = _reactive_pick(None, 1024, "halton", ticks=400)
-    assert task in ("pick", "place") and dist < 0.08, f"task {task}, closest approach {dist:.3f} m after {n} ticks"
+    """Same episode on the CUDA path: reach, grasp, carry, switch to place (the trajectory is not the oracle's: closed
+    loops amplify rounding)."""
+    task, dist, n = _reactive_pick(None, 1024, "halton", ticks=450)
+    assert task == "place" and dist < 0.05, f"task {task}, cubeA {dist:.3f} m from the pre-place pose after {n} ticks"

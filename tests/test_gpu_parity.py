@@ -33,7 +33,7 @@ def test_native_reproduces_reference_goldens(name):
     contact = name in ("nav_obstacle", "push_k256_t20", "pull_k256_t20", "push_pull_mm", "panda_pick")
     bad = 0.02 if contact else 0.0
     if name == "panda_pick":
-        bad = 0.05   # grasp state, 64 samples: stick / slip amplifies fp32 rounding (see test_team_and_thread_kernels_agree)
+        bad = 0.01   # grasp state: accumulated + warm-started impulses keep fp32 reordering from growing (round 1: 5 %)
     for i in range(int(g["calls"])):
         action, cost_total, info = tick(n, g, i)
         st = n.get_planner_state()
@@ -252,14 +252,12 @@ def test_team_and_thread_kernels_agree(task, mm, shelf):
     """The lane-cooperative (8 and 16 lanes per sample) and the thread-per-sample rollout kernels apply the same impulses
     in the same order (only the summation order of the reported contact forces differs), and both follow the oracle.
     `pick` starts with the fingers closed around cubeA (finger / cube / table contacts in every rollout). Stick /
-    slip contact dynamics amplify fp32 rounding differences (FMA contraction, SFU division) step by step: measured on
-    B200 (4 link sweeps per pass), 4-12 % of the samples deviate from the oracle by more than 1e-3 somewhere in a 16-step
-    rollout (9 % for the thread-per-sample kernel, 12 % for both team shapes, which agree with each other) while the
-    median deviation stays below 2e-4 and the resulting actions agree to 1e-4; the test allows 15 % and bounds the
-    median."""
+    slip contact dynamics amplify fp32 rounding differences (FMA contraction, SFU division); with the accumulated,
+    warm-started impulse solver the budget is 2 % of the samples (the non-accumulated solver of round 1 needed 15 %)
+    and the median deviation is bounded."""
     O.set_threads(8)
     case = ("x", "panda_env", task, None, 512, 16, mm, shelf, None)
-    budget = 0.15 if task == "pick" else 0.005
+    budget = 0.02 if task == "pick" else 0.005
     res = {}
     for lanes in (1, 8, 16):
         cfg, o, n = _setup(case, A.NOISE_PHILOX)

@@ -19,10 +19,10 @@ def test_oracle_reproduces_reference(name):
     o.set_noise_table(g["delta"])
     mm = bool(g["multi_modal"])
     K, T, nu = int(g["K"]), int(g["T"]), int(g["nu"])
-    # panda_pick starts in a grasp (finger / cube / table contacts in every rollout, 4 link sweeps per pass): stick / slip
-    # amplifies the 1-ulp differences between the reference's torch arithmetic for the perturbed actions and the C
-    # loops, so one or two of the 64 samples may end a rollout with a visibly different cost; everything else is exact
-    bad = 0.04 if name == "panda_pick" else 0.0
+    # panda_pick starts in a grasp (finger / cube / table contacts in every rollout): with accumulated, warm-started
+    # impulses the 1-ulp differences between the reference's torch arithmetic for the perturbed actions and the C loops
+    # no longer grow into visible cost differences (the non-accumulated solver of round 1 needed a 4 % budget here)
+    bad = 0.0
     for i in range(int(g["calls"])):
         action, cost_total, info = tick(o, g, i)
         st = o.get_planner_state()

@@ -1,0 +1,78 @@
+"""The rollout kernels' DEVICE CODE against the oracle without a GPU: tests/emu compiles panda_team.cuh (the body of
+k_rollout_team) and panda_env.cuh (panda_step / panda_cost, the thread-per-sample path) for the host and runs the
+team kernel 32 lanes in lock step (fibers; every warp collective checks that all lanes meet at the same source line,
+so a non-uniform branch around a shuffle -- undefined behaviour on the GPU -- fails here). Open-loop rollouts of the
+same actions from the same state must reproduce the oracle's costs and state rows: rest state (both cubes asleep),
+fingers closing on cubeA and carrying it (accumulated impulses, warm start, cube / table contact), the pre-grasp
+straddle, reach with the producer rows (single- and multi-modal, cube on the shelf), place."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+
+import oracle_py as O  # noqa: E402
+import team_emu as E  # noqa: E402
+from m3p2i_b200 import _abi as A  # noqa: E402
+from m3p2i_b200 import scene as S  # noqa: E402
+
+GRASP_Q = [-0.21448, 1.040633, -0.091726, -1.527796, 0.144743, 2.56178, 0.807333]
+
+
+def _case(task, fingers, K, T, shelf=False, mm=False, seed=0, sigma=1.0):
+    cfg = S.make_cfg("panda_env", task, None, K, T, multi_modal=mm, cube_on_shelf=shelf)
+    c = S.build_config(cfg, noise_mode=A.NOISE_TABLE, seed=0)
+    scene = S.build_panda_scene()
+    actors = S.default_actors("panda_env")
+    dof, root = S.initial_dof_state(actors).copy(), S.initial_root_state(actors, shelf).copy()
+    if not shelf:
+        root[S.actor_index(actors, "cubeA"), 2] -= 0.0095
+    root[S.actor_index(actors, "cubeB"), 2] -= 0.0095
+    if fingers is not None:
+        dof[0::2] = GRASP_Q + [fingers, fingers]
+    cb = root[S.actor_index(actors, "cubeB")]
+    goal = np.concatenate([cb[:3] + np.array([0, 0, 0.055], np.float32), cb[3:7]]).astype(np.float32) if task == "pick" \
+        else np.zeros(7, np.float32)
+    rng = np.random.default_rng(seed)
+    a = np.clip(rng.normal(size=(K, 1, 9)) * sigma + 0.3 * sigma * rng.normal(size=(K, T, 9)), -2, 2).astype(np.float32)
+    grip = {"pick": "close", "reach": "open", "place": "open"}[task]
+    a[:, :, 7:] = -1.5 if grip == "close" else 1.5
+    o = O.Oracle(c, scene)
+    o.set_state(dof, root)
+    o.set_objective(task, goal, grip)
+    st_o, ch_o = o.rollout_actions(a)
+    o.close()
+    return c, scene, task, goal, grip, dof, root, a, st_o, ch_o
+
+
+@pytest.mark.parametrize("task,fingers,K,T,lanes,shelf,mm,sigma", [
+    ("pick", None, 12, 6, 8, False, False, 1.0),     # arm away from the cubes: both asleep, bit-equal costs
+    ("pick", 0.027, 16, 10, 8, False, False, 1.0),   # closed on cubeA: squeeze, lift, table contact
+    ("pick", 0.027, 8, 10, 16, False, False, 1.0),
+    ("pick", 0.04, 16, 10, 8, False, False, 0.5),    # open fingers astride cubeA closing on it
+    ("reach", 0.04, 12, 8, 16, False, False, 0.5),
+    ("reach", None, 16, 6, 8, True, True, 1.0),
+    ("place", 0.027, 8, 9, 8, False, False, 1.0),
+])
+def test_team_device_code_matches_oracle(task, fingers, K, T, lanes, shelf, mm, sigma):
+    c, scene, task, goal, grip, dof, root, a, st_o, ch_o = _case(task, fingers, K, T, shelf, mm, sigma=sigma)
+    st_e, ch_e, env_e, ncoll = E.rollout_actions(c, scene, task, goal, grip, dof, root, a, lanes)
+    assert ncoll > 0
+    assert np.allclose(st_e, st_o, rtol=1e-5, atol=1e-5)
+    bad = ~np.isclose(ch_e, ch_o, rtol=1e-3, atol=5e-3)
+    assert not bad.any(), f"{bad.sum()} of {bad.size} step costs differ, max {np.abs(ch_e - ch_o).max()}"
+    if fingers is None and task == "pick":
+        assert np.array_equal(ch_e, ch_o)   # nothing but the arm moves
+    if task != "reach":
+        st_t, ch_t, env_t = E.thread_rollout_actions(c, scene, task, goal, grip, dof, root, a)
+        assert np.allclose(st_t, st_o, rtol=1e-5, atol=1e-5)
+        assert np.isclose(ch_t, ch_o, rtol=1e-3, atol=5e-3).all(), np.abs(ch_t - ch_o).max()
+        assert np.abs(env_t[:, :44] - env_e[:, :44]).max() < 5e-3   # end states of the two kernel shapes
+
+
+def test_contact_rich_case_has_contacts():
+    """The grasp case above is not vacuous: the oracle's rollouts contain collision-cost steps and the cube moves."""
+    *_, st_o, ch_o = _case("pick", 0.027, 16, 10)
+    assert (ch_o > 900).any() and (ch_o < 900).any()
