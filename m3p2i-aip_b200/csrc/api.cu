@@ -112,9 +112,11 @@ struct M3P2IHandle_ {
   DevBuf<Stats> stats;
   DevBuf<M3P2ICommandInfo> info;
   bool have_noise = false, have_row0 = false, have_filt = false, have_evr = false;
-  // pinned host staging
+  // pinned host staging: results (grows on demand) and, separately, the packed base env written by set_state and
+  // uploaded lazily (it must survive a reallocation of the result buffer)
   float* pin = nullptr;
   size_t pin_n = 0;
+  float* pin_base = nullptr;   // [64]
   M3P2ICommandInfo last_info;
   // multi-GPU
   ncclComm_t comm = nullptr;
@@ -347,8 +349,8 @@ int check_ready(const H* h) {
 
 int upload_base(H* h) {
   if (!h->base_dirty) return 0;
-  // h->pin[0..nf) holds the packed base env (written by set_state)
-  CK(cudaMemcpyAsync(h->base.p, h->pin, sizeof(float) * h->nf, cudaMemcpyHostToDevice, h->stream));
+  // h->pin_base[0..nf) holds the packed base env (written by set_state)
+  CK(cudaMemcpyAsync(h->base.p, h->pin_base, sizeof(float) * h->nf, cudaMemcpyHostToDevice, h->stream));
   h->base_dirty = false;
   return 0;
 }
@@ -425,9 +427,9 @@ int reduce_partials(H* h) {
 int fetch(H* h, float* out_action, float* out_cost_total, M3P2ICommandInfo* info, bool unfiltered) {
   const size_t TN = (size_t)h->cfg.horizon * h->cfg.nu, K = h->cfg.num_samples;
   const size_t need = 2 * TN + sizeof(M3P2ICommandInfo) / sizeof(float) + 1 + (out_cost_total ? K : 0);
-  int rc = ensure_pin(h, std::max<size_t>(need + 64, 256));
+  int rc = ensure_pin(h, std::max<size_t>(need, 256));
   if (rc) return rc;
-  float* p = h->pin + 64;  // the first 64 floats stage the base env
+  float* p = h->pin;
   CK(cudaMemcpyAsync(p, h->result.p, sizeof(float) * 2 * TN, cudaMemcpyDeviceToHost, h->stream));
   M3P2ICommandInfo* pi = reinterpret_cast<M3P2ICommandInfo*>(p + 2 * TN);
   CK(cudaMemcpyAsync(pi, h->info.p, sizeof(M3P2ICommandInfo), cudaMemcpyDeviceToHost, h->stream));
@@ -437,7 +439,12 @@ int fetch(H* h, float* out_action, float* out_cost_total, M3P2ICommandInfo* info
   *perr = 0u;
   if (h->peer_on) CK(cudaMemcpyAsync(perr, h->ref_flags.p + 4, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  if (*perr) return fail(M3P2I_ERR_STATE, "peer exchange timed out: a rank did not deliver its costs / partial sums");
+  if (*perr) {
+    // report once: clear the flag so that later commands are judged on their own exchange
+    CK(cudaMemsetAsync(h->ref_flags.p + 4, 0, sizeof(unsigned), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return fail(M3P2I_ERR_STATE, "peer exchange timed out: a rank did not deliver its costs / partial sums");
+  }
   if (out_action) memcpy(out_action, unfiltered ? p + TN : p, sizeof(float) * TN);
   if (out_cost_total) memcpy(out_cost_total, pc, sizeof(float) * K);
   const float kms = h->last_info.kernel_ms, rms = h->last_info.rollout_ms;
@@ -578,6 +585,10 @@ int m3p2i_create(const M3P2IConfig* cfg, int device, m3p2i_handle* out) {
   memset(&h->last_info, 0, sizeof(h->last_info));
   int rc = ensure_pin(h, 4096);
   if (rc) { m3p2i_destroy(h); return rc; }
+  if (cudaMallocHost(&h->pin_base, sizeof(float) * 64) != cudaSuccess) {
+    m3p2i_destroy(h);
+    return fail(M3P2I_ERR_CUDA, "m3p2i_create: cudaMallocHost failed");
+  }
   *out = h;
   return 0;
 }
@@ -595,6 +606,7 @@ void m3p2i_destroy(m3p2i_handle h) {
   h->cost_total.release(); h->result.release(); h->links.release(); h->scratch.release(); h->states.release();
   h->refs.release(); h->ref_flags.release(); h->stats.release(); h->info.release();
   if (h->pin) cudaFreeHost(h->pin);
+  if (h->pin_base) cudaFreeHost(h->pin_base);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->evr) cudaEventDestroy(h->evr);
@@ -661,7 +673,7 @@ int m3p2i_set_state(m3p2i_handle h, const float* dof, const float* root) {
   }
   // the staging slot may still be in flight from the previous tick
   CK(cudaStreamSynchronize(h->stream));
-  pack_env(h, dof, root, h->pin);
+  pack_env(h, dof, root, h->pin_base);
   h->base_dirty = true;
   h->have_state = true;
   h->env_live = false;

@@ -111,12 +111,14 @@ class MPPI():
         from m3p2i_aip.utils.isaacgym_utils.isaacgym_wrapper import IsaacGymWrapper
         self.noise_abs_cost = bool(getattr(m, "noise_abs_cost", False))
         self.noise_sigma_inv = torch.inverse(self.noise_sigma)
+        mu = getattr(m, "noise_mu", None)
+        self.noise_mu = torch.tensor(mu, dtype=torch.float32) if mu else torch.zeros(self.nu)
         self._rng = torch.Generator().manual_seed(self.seed_val)
         self.U = None
-        if self.mppi_mode == "simple":
-            m.fused = False   # classic MPPI resamples its noise every call and runs through the callbacks
+        # classic MPPI resamples its noise every call and runs through the callbacks (the caller's cfg is not touched)
+        fused_opt = self.mppi_mode != "simple" and bool(getattr(m, "fused", True))
         self.fused = (isinstance(sim, IsaacGymWrapper) and isinstance(obj, Objective)
-                      and getattr(running_cost, "__self__", None) is owner and getattr(m, "fused", True)
+                      and getattr(running_cost, "__self__", None) is owner and fused_opt
                       and sim.num_envs == self.K)
         noise_mode = {"philox": A.NOISE_PHILOX, "philox-spline": A.NOISE_PHILOX_SPLINE}.get(self.sampling_method, A.NOISE_TABLE)
         if self.fused:
@@ -158,8 +160,9 @@ class MPPI():
         if self.sampling_method == "halton":
             return torch.from_numpy(mppi_utils.halton_spline_table(sample_shape, self.T, self.nu))
         if self.sampling_method == "random":
-            g = torch.Generator().manual_seed(self.seed_val)
-            return torch.randn(sample_shape, self.T, self.nu, generator=g) * torch.sqrt(torch.diagonal(self.noise_sigma))
+            # noise_dist.sample((K, T)) of mppi.py:479-480: fresh N(noise_mu, noise_sigma) draws on every command,
+            # from the planner's own generator (full covariance through its Cholesky factor)
+            return self._sample_noise(sample_shape, self.T) + self.noise_mu
         raise ValueError(f"unknown sampling_method {self.sampling_method!r}")
 
     def _sample_noise(self, *shape):

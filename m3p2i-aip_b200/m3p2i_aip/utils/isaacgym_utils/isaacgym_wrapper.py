@@ -219,6 +219,9 @@ class IsaacGymWrapper:
 
     # ------------------------------------------------------------------ setters
     def set_dof_state_tensor(self, u):
+        # bring BOTH host mirrors up to date first: the next push writes dof and root together, and Isaac Gym's
+        # set_dof_state_tensor never touches the root states (a stale root mirror would rewind every actor)
+        self._refresh()
         u = torch.as_tensor(u, dtype=torch.float32).reshape(self.num_envs, -1)
         if u.data_ptr() != self.__dof.data_ptr():
             self.__dof.copy_(u)
@@ -226,6 +229,7 @@ class IsaacGymWrapper:
         self._host_dirty = False
 
     def set_actor_root_state_tensor(self, u):
+        self._refresh()   # see set_dof_state_tensor: the dof mirror must not be stale when the pair is pushed
         u = torch.as_tensor(u, dtype=torch.float32).reshape(self.num_envs, -1, 13)
         if u.data_ptr() != self.__root.data_ptr():
             self.__root.copy_(u)

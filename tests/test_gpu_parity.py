@@ -253,8 +253,9 @@ def test_team_and_thread_kernels_agree(task, mm, shelf):
     in the same order (only the summation order of the reported contact forces differs), and both follow the oracle.
     `pick` starts with the fingers closed around cubeA (finger / cube / table contacts in every rollout). Stick /
     slip contact dynamics amplify fp32 rounding differences (FMA contraction, SFU division); with the accumulated,
-    warm-started impulse solver the budget is 2 % of the samples (the non-accumulated solver of round 1 needed 15 %)
-    and the median deviation is bounded."""
+    warm-started impulse solver 0.2 - 0.6 % of the samples deviate by more than 1e-3 somewhere in a rollout on B200 and
+    none flips the collision cost (tests/experiments/grasp_parity.py; the non-accumulated solver of round 1 needed a
+    15 % budget); the test allows 2 % and bounds the median."""
     O.set_threads(8)
     case = ("x", "panda_env", task, None, 512, 16, mm, shelf, None)
     budget = 0.02 if task == "pick" else 0.005

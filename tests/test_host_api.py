@@ -197,3 +197,67 @@ def test_skip_rollout_readback_is_equivalent_for_the_run_tamp_flow():
         reads.append(n["reads"])
     assert torch.equal(outs[0], outs[1])
     assert reads[1] == 0 and reads[0] >= 2
+
+
+def test_random_sampling_draws_fresh_noise_every_command():
+    """sampling_method='random' (mppi.py:386-388,479-480): noise_dist.sample((K, T)) is drawn anew on EVERY command,
+    from N(noise_mu, noise_sigma) with the full covariance."""
+    from m3p2i_b200 import scene as S
+    cfg = S.make_cfg("point_env", "navigation", [1.0, 1.0], 64, 12)
+    cfg.mppi.sampling_method = "random"
+    cfg.mppi.noise_sigma = [[2.0, 0.6], [0.6, 1.0]]
+    tamp = Tamp(cfg, O.Oracle.for_sim, True)
+    mp = tamp.motion_planner
+    actors = S.default_actors("point_env")
+    dof, root = torch.from_numpy(S.initial_dof_state(actors)), torch.from_numpy(S.initial_root_state(actors))
+    tamp.run_tamp(dof, root, "navigation", torch.tensor([1.0, 1.0]), False)
+    d0 = mp.delta.clone()
+    tamp.run_tamp(dof, root, "navigation", torch.tensor([1.0, 1.0]), False)
+    d1 = mp.delta.clone()
+    assert d0.shape == (64, 12, 2) and not torch.equal(d0, d1)
+    big = torch.cat([mp.get_samples(64) for _ in range(40)]).reshape(-1, 2)
+    assert np.allclose(np.cov(big.numpy().T), np.array(cfg.mppi.noise_sigma), atol=0.08)
+    tamp.sim.stop_sim()
+
+
+def test_state_setters_do_not_rewind_the_other_tensor():
+    """IsaacGym's set_dof_state_tensor leaves the root states alone (and vice versa): after step(), setting only the DOF
+    state from an external tensor must not push a stale root mirror back to the device."""
+    from m3p2i_b200 import scene as S
+    cfg = S.make_cfg("point_env", "push", [0.0, 3.5], 1, 12)
+    sim = wrapper.IsaacGymWrapper(cfg.isaacgym, "point_env", num_envs=1, device="cpu", backend_factory=O.Oracle.for_sim)
+    bi = int(sim._get_actor_index_by_name("box"))
+    sim._dof_state[0, 2] = 1.5          # robot just below the block, pushing +y
+    sim.set_dof_state_tensor(sim._dof_state)
+    for _ in range(40):
+        sim.set_dof_velocity_target_tensor(torch.tensor([[0.0, 2.0]]))
+        sim.step()
+    external = torch.tensor([[0.0, 0.0, 1.0, 0.0]])
+    sim.set_dof_state_tensor(external)  # no read of _dof_state / _root_state in between
+    for _ in range(5):
+        sim.set_dof_velocity_target_tensor(torch.tensor([[0.0, 0.0]]))
+        sim.step()
+    y_before_reset = 2.0
+    assert float(sim._root_state[0, bi, 1]) > y_before_reset + 0.2, "the pushed block was rewound by the DOF-only reset"
+    assert abs(float(sim._dof_state[0, 2]) - 1.0) < 0.05
+    sim.stop_sim()
+
+
+def test_wire_frames_are_safe_and_raw_frames_round_trip():
+    """utils/data_transfer.py: torch.save frames decode without arbitrary unpickling; raw fp32 frames round-trip."""
+    import io
+    import os
+    from m3p2i_aip.utils import data_transfer as D
+    t = torch.randn(1, 7, 13)
+    assert torch.equal(D.bytes_to_torch(D.torch_to_bytes(t)), t)
+    assert torch.equal(D.bytes_to_torch(D.raw_to_bytes(t)), t)
+    assert len(D.raw_to_bytes(t)) < len(D.torch_to_bytes(t)) / 2
+    assert np.array_equal(D.bytes_to_numpy(D.numpy_to_bytes(np.arange(6, dtype=np.float32))), np.arange(6, dtype=np.float32))
+
+    class Evil:
+        def __reduce__(self):
+            return (os.getcwd, ())
+    buf = io.BytesIO()
+    torch.save(Evil(), buf)
+    with pytest.raises(Exception):
+        D.bytes_to_torch(buf.getvalue())

@@ -8,6 +8,8 @@ import sys
 
 sass_csv, dis, kern, attr_file = sys.argv[1:5]
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
+import os
+skip_from = int(os.environ.get('SKIP_FROM', '0'))   # ignore frames at or after this line (a thin wrapper at the end of the file)
 func, chain, addr2chain = None, [], {}
 pending = []
 for ln in open(dis):
@@ -43,7 +45,7 @@ for r in rows[2:]:
     ch = addr2chain.get(a - base, [])
     key = None
     for f, l in reversed(ch):        # outermost frame first
-        if f == attr_file:
+        if f == attr_file and not (skip_from and l >= skip_from):
             key = l
             break
     if key is None:
