@@ -2,14 +2,21 @@
 """bench.py -- sample-steps/s of one MPPI command() (the hot path of BASELINE.json) on N B200s.
 
 A step is one planner tick: noise -> perturbation -> K x H rollout (dynamics + cost) -> softmin -> mean update.
-Workload: config_panda reactive pick, 7-DoF Panda + cube, K=4096 per GPU, H=32 (BASELINE.json configs[3]; at N>1
-K is sharded, K_global = 4096*N, which at N=8 is configs[4]'s K=32768).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3|c4|c4_grasp|c5] [--impl native|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Prints ONE JSON line on rank 0 (see the keys below). `--impl reference` times the CPU oracle port of the same path
-on the host cores (the reference's own rollout needs IsaacGym, which cannot be installed: DESIGN.md).
+Workloads (BASELINE.json configs; K is per GPU, sharded commands run K_global = K * N):
+    c1        navigation, point robot, K=200 H=12
+    c2        push, point robot + block, K=1024 H=20
+    c3        push_pull multi_modal, 2 x 2048, H=20
+    c4        config_panda reactive pick, K=4096 H=32, arm at its initial pose        <- default at N = 1 (the headline)
+    c4_grasp  the same command with the fingers closed around cubeA (every rollout is contact-rich)
+    c5        config_panda multi_modal=True cube_on_shelf=True (reach), K=4096 per GPU, H=32: K_global = 32768 at N = 8
+                                                                                        <- default at N > 1
+Prints ONE JSON line on rank 0. `--impl reference` times the reference's own CPU implementation of the same command:
+the UNMODIFIED reference Python (baseline/_ref: M3P2I.command + Objective.compute_cost, device='cpu') over the sim
+facade, with the oracle's C integrator standing in for IsaacGym/PhysX (not installable), on all host cores.
 """
 import argparse
 import json
@@ -26,24 +33,49 @@ for p in (os.path.join(ROOT, "m3p2i-aip_b200"), os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-K_PER_GPU = 4096
-HORIZON = 32
-WORKLOAD = "config_panda reactive pick, 7-DoF Panda + cube, K=4096 per GPU, H=32"
+GRASP_Q = [-0.21448, 1.040633, -0.091726, -1.527796, 0.144743, 2.56178, 0.807333, 0.027, 0.027]
+CONFIGS = {
+    "c1": dict(env="point_env", task="navigation", goal=[-3.0, 3.0], K=200, T=12, mm=False,
+               workload="navigation task, point-robot 2D, K=200 H=12 single-mode (BASELINE configs[0])"),
+    "c2": dict(env="point_env", task="push", goal=[-1.0, -1.0], K=1024, T=20, mm=False, robot=[0.2, 2.45],
+               workload="push task, point-robot with box contact, K=1024 H=20 (BASELINE configs[1])"),
+    "c3": dict(env="point_env", task="push_pull", goal=[-3.75, -3.75], K=4096, T=20, mm=True, robot=[0.3, 2.4],
+               workload="push_pull multi_modal=True, 2 modes x K=2048 H=20 (BASELINE configs[2])"),
+    "c4": dict(env="panda_env", task="pick", K=4096, T=32, mm=False, grip="close",
+               workload="config_panda reactive pick, 7-DoF Panda + cube, K=4096 per GPU, H=32 (BASELINE configs[3])"),
+    "c4_grasp": dict(env="panda_env", task="pick", K=4096, T=32, mm=False, grip="close", q=GRASP_Q,
+                     workload="config_panda reactive pick, K=4096 per GPU, H=32, fingers closed around cubeA (contact-rich "
+                              "state of configs[3])"),
+    "c5": dict(env="panda_env", task="reach", K=4096, T=32, mm=True, shelf=True, grip="open",
+               workload="config_panda multi_modal=True cube_on_shelf=True (reach), K=4096 per GPU, H=32 "
+                        "(BASELINE configs[4]: K_global=32768 over 8 GPUs)"),
+}
 # algorithmic HBM bytes per sample-step (DESIGN.md "Algorithmic bytes"): the rollout kernel writes the action row
-# (9 f32), the float4 state row and the cost; the weighted-sum pass re-reads the action row.
-B_ROLLOUT = 4 * 9 + 16 + 4          # 56 B, fused rollout kernel (Philox noise: no table read)
-B_PATH = B_ROLLOUT + 4 * 9          # 92 B, whole command
+# (nu f32), the float4 state row and the cost; the weighted-sum pass re-reads the action row.
+B_ROLLOUT = {"point_env": 4 * 2 + 16 + 4, "panda_env": 4 * 9 + 16 + 4}
+B_PATH = {"point_env": 4 * 2 + 16 + 4 + 4 * 2, "panda_env": 4 * 9 + 16 + 4 + 4 * 9}
 
 
-def scene_inputs():
+def scene_inputs(conf=None):
+    """(dof_state, root_state, goal) of a workload: the reference's initial scene, cubes at rest."""
     from m3p2i_b200 import scene as S
-    actors = S.default_actors("panda_env")
-    dof, root = S.initial_dof_state(actors).copy(), S.initial_root_state(actors).copy()
+    conf = conf or CONFIGS["c4"]
+    actors = S.default_actors(conf["env"])
+    shelf = bool(conf.get("shelf"))
+    dof, root = S.initial_dof_state(actors).copy(), S.initial_root_state(actors, shelf).copy()
+    if conf["env"] == "point_env":
+        if conf.get("robot"):
+            dof[0], dof[2] = conf["robot"]
+        return dof, root, np.asarray(conf["goal"], np.float32)
     # cubes resting on the table, as in a running episode
-    root[S.actor_index(actors, "cubeA"), 2] -= 0.0095
+    if not shelf:
+        root[S.actor_index(actors, "cubeA"), 2] -= 0.0095
     root[S.actor_index(actors, "cubeB"), 2] -= 0.0095
+    if conf.get("q"):
+        dof[0::2] = conf["q"]
     cb = root[S.actor_index(actors, "cubeB")]
-    goal = np.concatenate([cb[:3] + np.array([0, 0, 0.055], np.float32), cb[3:7]]).astype(np.float32)
+    goal = np.concatenate([cb[:3] + np.array([0, 0, 0.055], np.float32), cb[3:7]]).astype(np.float32) \
+        if conf["task"] == "pick" else np.zeros(7, np.float32)
     return dof, root, goal
 
 
@@ -63,8 +95,10 @@ class stdout_to_stderr:
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons during the timed region (B200_PROFILING.md): NVML polled every 5 ms in this
-    process (nvidia_ml_py), or nvidia-smi every 100 ms when NVML cannot be loaded."""
+    """SM clock and throttle reasons while the benchmark runs (B200_PROFILING.md): NVML polled every 50 ms in this
+    process (nvidia_ml_py), or nvidia-smi every 200 ms when NVML cannot be loaded. Started BEFORE the warm-up so that
+    the thread is in steady state during the timed region; the coarse period keeps it from competing with the
+    launching thread for the GIL."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -90,23 +124,26 @@ class ClockSampler(threading.Thread):
                 if self.nvml is not None:
                     sm = int(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
                     mask = int(self.reasons_fn(self.handle))
-                    self.rows.append([str(sm), str(self.max_sm)] + ["Active" if mask & b else "Not Active" for b in self.BITS])
-                    self.stop_flag.wait(0.005)
+                    self.rows.append([time.perf_counter(), str(sm), str(self.max_sm)] +
+                                     ["Active" if mask & b else "Not Active" for b in self.BITS])
+                    self.stop_flag.wait(0.05)
                     continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                                       str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                    self.rows.append([time.perf_counter()] + [x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.2)
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        """clocks over [t0, t1] (perf_counter; the timed regions), all samples if that window caught none"""
         self.stop_flag.set()
         self.join(timeout=6)
-        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        reasons = sorted({self.NAMES[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i] == "Active"})
+        rows = [r for r in self.rows if t0 is None or t0 <= r[0] <= t1] or self.rows
+        sm = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
+        mx = [int(r[2]) for r in rows if len(r) > 2 and r[2].isdigit()]
+        reasons = sorted({self.NAMES[i] for r in rows for i in range(4) if len(r) > 3 + i and r[3 + i] == "Active"})
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
@@ -118,42 +155,46 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch from the committed ncu --set full capture
-    (profiles/), in bytes; None if the summary is missing."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_rollout_team_summary.csv")
+NCU_SUMMARY = {"c4": "r02_ncu_rollout_team_c4_summary.csv"}
+
+
+def ncu_numbers(name):
+    """(dram bytes per launch, issue-slot utilisation in percent) of the rollout kernel from the committed
+    ncu --set full summary of this workload (profiles/), or (None, None)."""
+    path = os.path.join(ROOT, "profiles", NCU_SUMMARY.get(name, "-"))
     if not os.path.exists(path):
-        return None
+        return None, None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot = 0.0
+    tot, issue = 0.0, None
     for line in open(path):
         parts = line.strip().split(",")
         if len(parts) >= 4 and parts[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(parts[-1]) * scale.get(parts[-2], 1.0)
-    return tot or None
+        if len(parts) >= 4 and parts[-3] == "smsp__issue_active.avg.pct_of_peak_sustained_active":
+            issue = float(parts[-1])
+    return (tot or None), issue
 
 
-def cpu_oracle_rate(threads, seconds=12.0, K=K_PER_GPU, T=HORIZON, min_steps=2, warmup=1):
-    """The CPU port of the same path (oracle/), OpenMP over samples, timed for about `seconds`."""
+def cpu_port_rate(conf, threads, seconds=5.0):
+    """The C port of the same path (oracle/, OpenMP over samples), timed for about `seconds`."""
     import oracle_py as O
     from m3p2i_b200 import _abi as A
     from m3p2i_b200 import scene as S
     O.set_threads(threads)
-    cfg = S.make_cfg("panda_env", "pick", None, K, T)
-    o = O.Oracle(S.build_config(cfg, noise_mode=A.NOISE_PHILOX, seed=0), S.build_panda_scene())
+    K, T = conf["K"], conf["T"]
+    dof, root, goal = scene_inputs(conf)
+    cfg = S.make_cfg(conf["env"], conf["task"], goal.tolist(), K, T, multi_modal=conf["mm"], cube_on_shelf=bool(conf.get("shelf")))
+    scene = S.build_point_scene() if conf["env"] == "point_env" else S.build_panda_scene()
+    o = O.Oracle(S.build_config(cfg, noise_mode=A.NOISE_PHILOX, seed=0), scene)
     o.set_filter_matrix(S.savgol_matrix(T))
-    dof, root, goal = scene_inputs()
-    o.set_objective("pick", goal, "close")
-    times = []
-    t_end = time.perf_counter() + seconds
-    n = 0
-    while n < warmup + min_steps or time.perf_counter() < t_end:
+    o.set_objective(conf["task"], goal, conf.get("grip"))
+    times, t_end, n = [], time.perf_counter() + seconds, 0
+    while n < 3 or time.perf_counter() < t_end:
         o.set_state(dof, root)
         t0 = time.perf_counter()
         o.command()
-        dt = time.perf_counter() - t0
-        if n >= warmup:
-            times.append(dt)
+        if n >= 1:
+            times.append(time.perf_counter() - t0)
         n += 1
         if len(times) >= 200:
             break
@@ -161,93 +202,78 @@ def cpu_oracle_rate(threads, seconds=12.0, K=K_PER_GPU, T=HORIZON, min_steps=2, 
     return K * T / float(np.median(times)), len(times), float(np.median(times))
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only)."""
+def cpu_reference_python(conf, K, threads, steps, warmup):
+    """Per-command seconds of the unmodified reference Python over the facade (oracle/reference_rig.py)."""
+    import reference_rig as R
+    dof, root, goal = scene_inputs(conf)
+    return R.time_reference(conf["env"], conf["task"], goal.tolist(), K, conf["T"], dof, root, multi_modal=conf["mm"],
+                            cube_on_shelf=bool(conf.get("shelf")), steps=steps, warmup=warmup, threads=threads)
+
+
+REF_KIND = "reference-python+port-dynamics"
+REF_NOTE = ("unmodified reference M3P2I.command + Objective.compute_cost (baseline/_ref, torch CPU tensors, all host cores) "
+            "driven as scripts/reactive_tamp.py does, over the sim facade with the oracle's C integrator standing in for "
+            "IsaacGym/PhysX (closed binary, not installable); noise table injected (the first-call scipy spline loop is not timed)")
+
+
+def run_reference(args, rank, world, name, conf):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    import oracle_py as O
-    from m3p2i_b200 import _abi as A
-    from m3p2i_b200 import scene as S
-    O.set_threads(cores)
-    Kg = K_PER_GPU * args.gpus
-    # bounded sample: the full K of one GPU's shard per step (the port's cost is linear in K)
-    Ks = K_PER_GPU
-    cfg = S.make_cfg("panda_env", "pick", None, Ks, HORIZON)
-    o = O.Oracle(S.build_config(cfg, noise_mode=A.NOISE_PHILOX, seed=0), S.build_panda_scene())
-    o.set_filter_matrix(S.savgol_matrix(HORIZON))
-    dof, root, goal = scene_inputs()
-    o.set_objective("pick", goal, "close")
-    for _ in range(args.warmup):
-        o.set_state(dof, root)
-        o.command()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        o.set_state(dof, root)
-        o.command()
-    dt = (time.perf_counter() - t0) / args.steps
-    value = Ks * HORIZON / dt
-    line = {"impl": "reference", "metric": "sample-steps/sec (K x H per command)", "value": value, "unit": "sample-steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "K_global": Kg, "H": HORIZON, "noise": "philox4x32-10",
-                       "note": "CPU port of the reference path (oracle/, OpenMP over samples); the reference's own rollout "
-                               "is IsaacGym/PhysX which is not installable; throughput of the port is independent of K"},
-            "cpu_baseline": {"value": value, "unit": "sample-steps/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} commands of K={Ks}, H={HORIZON} (one GPU's shard)"},
-            "e2e": {"value": value, "unit": "sample-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+    T = conf["T"]
+    Kg = conf["K"] * max(args.gpus, 1)
+    line = {"impl": "reference", "metric": "sample-steps/sec (K x H per command)", "unit": "sample-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "gpu_launches": 0}
+    try:
+        import reference_rig as R
+        have_ref = R.reference_dir() is not None
+    except Exception:
+        have_ref = False
+    if have_ref:
+        # full K_global when the whole run fits in a few minutes, else one GPU's shard per step (the reference's cost
+        # is linear in K): decided from one untimed command
+        K_run, scope = Kg, "full K_global"
+        t_probe = cpu_reference_python(conf, K_run, cores, 1, 0)[0][0]
+        if t_probe * (args.steps + args.warmup) > 150.0 and Kg > conf["K"]:
+            K_run, scope = conf["K"], "per-shard: one GPU's K per step (the reference's cost is linear in K)"
+        times, src = cpu_reference_python(conf, K_run, cores, args.steps, args.warmup)
+        dt = float(np.mean(times))
+        value = K_run * T / dt
+        kind, sample = REF_KIND, f"{args.steps} commands of K={K_run}, H={T} ({scope}); reference from {os.path.relpath(src, ROOT)}"
+        note = REF_NOTE
+        med = float(np.median(times))
+    else:
+        v, n, med = cpu_port_rate(conf, cores, seconds=max(5.0, 0.05 * args.steps))
+        dt, value, K_run, scope = med, v, conf["K"], "per-shard"
+        kind, sample = "port", f"{n} commands of K={conf['K']}, H={T}; baseline/_ref missing: C port of the path (oracle/, OpenMP)"
+        note = "baseline/_ref is absent (pip install --no-deps --target baseline/_ref <reference>): timed the C port instead"
+    line.update({"value": value, "ms_per_step": dt * 1e3, "ms_per_step_median": med * 1e3,
+                 "config": {"workload": conf["workload"] + ("" if scope == "full K_global" else f" [{scope}]"), "name": name,
+                            "K_global": Kg, "K_timed": K_run, "H": T, "note": note},
+                 "cpu_baseline": {"value": value, "unit": "sample-steps/s", "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": value, "unit": "sample-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N>1: exchange fused into the kernels over NVLink peer memory (default) or two NCCL collectives")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
-        args.gpus = world
-
-    import torch
+def build_planner(conf, world, rank, local_rank, exchange_arg):
     import torch.distributed as dist
     from m3p2i_b200 import _abi as A
     from m3p2i_b200 import native
     from m3p2i_b200 import scene as S
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        with stdout_to_stderr():
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-            dist.barrier()
-
-    Kg = K_PER_GPU * world
-    cfg = S.make_cfg("panda_env", "pick", None, Kg, HORIZON)
+    K, T = conf["K"], conf["T"]
+    Kg = K * world
+    dof, root, goal = scene_inputs(conf)
+    cfg = S.make_cfg(conf["env"], conf["task"], goal.tolist(), Kg, T, multi_modal=conf["mm"], cube_on_shelf=bool(conf.get("shelf")))
     cfg.mppi.sampling_method = "philox"
-    c = S.build_config(cfg, num_samples_local=K_PER_GPU, sample_offset=rank * K_PER_GPU, noise_mode=A.NOISE_PHILOX, seed=0)
-    planner = native.NativePlanner(c, S.build_panda_scene(), device=local_rank)
-    planner.set_filter_matrix(S.savgol_matrix(HORIZON))
+    c = S.build_config(cfg, num_samples_local=K, sample_offset=rank * K, noise_mode=A.NOISE_PHILOX, seed=0)
+    scene = S.build_point_scene() if conf["env"] == "point_env" else S.build_panda_scene()
+    planner = native.NativePlanner(c, scene, device=local_rank)
+    planner.set_filter_matrix(S.savgol_matrix(T))
     exchange = "none"
     if world > 1:
-        exchange = args.exchange
+        exchange = exchange_arg
         with stdout_to_stderr():
             if exchange == "peer":
                 from m3p2i_b200 import sharded
@@ -260,9 +286,56 @@ def main():
                 uid = [native.comm_unique_id() if rank == 0 else None]
                 dist.broadcast_object_list(uid, src=0)
                 planner.comm_init(rank, world, uid[0])
-    dof, root, goal = scene_inputs()
-    planner.set_objective("pick", goal, "close")
+    planner.set_objective(conf["task"], goal, conf.get("grip"))
     planner.set_state(dof, root)
+    return planner, exchange, dof, root
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="default: c4 on one GPU, c5 on several")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: exchange fused into the kernels over NVLink peer memory (default) or two NCCL collectives")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_for_default = max(world, args.gpus)
+    name = args.config or ("c4" if n_for_default == 1 else "c5")
+    conf = CONFIGS[name]
+    if args.impl == "reference":
+        run_reference(args, rank, world, name, conf)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+        args.gpus = world
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+
+    K, T, env = conf["K"], conf["T"], conf["env"]
+    Kg = K * world
+    planner, exchange, dof, root = build_planner(conf, world, rank, local_rank, args.exchange)
     # a stream torch owns, so that torch.cuda.Event brackets exactly the stream the kernels are launched on
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -279,10 +352,8 @@ def main():
     for _ in range(args.warmup):
         planner.command_resident()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    t_timed0 = time.perf_counter()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    roll_ms = []
     for i in range(args.steps):
         if flush is not None:
             flush.fill_(i & 1)  # > L2 (126 MB), outside the timed events
@@ -294,12 +365,19 @@ def main():
     if world > 1:
         dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)  # max over ranks, per step
     ms_per_step = float(step_ms.mean())
-    # rollout-kernel duration (CUDA events inside the library, same stream), L2 flushed before each launch
+    ms_median = float(step_ms.median())
+    # rollout-kernel duration and the waits of the peer exchange (CUDA events / globaltimer inside the library, same
+    # stream), L2 flushed before each launch
+    roll_ms, wait_j, wait_p = [], [], []
     for i in range(min(args.steps, 50)):
         if flush is not None:
             flush.fill_(i & 1)
+        if world > 1:
+            dist.barrier()   # every rank enters the command together: what is left in peer_wait_ms is rollout skew + exchange
         info = planner.command_resident(sync=True)
         roll_ms.append(info.rollout_ms)
+        wait_j.append(info.peer_wait_ms[0])
+        wait_p.append(info.peer_wait_ms[1])
     last = planner.command_resident(sync=True)
     launches_per_step, lanes = last.launches, int(last.rollout_lanes)
     barrier()
@@ -315,48 +393,115 @@ def main():
         planner.set_state(dof, root)                      # pinned staging + H2D inside
         act, _, _ = planner.command(want_cost=False)      # D2H of the action inside, synchronous
     barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device="cuda")
+    t_timed1 = time.perf_counter()
+    e2e_s = torch.tensor([(t_timed1 - t0) / n_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s)
-    clocks = sampler.summary()
-    h2d = 4 * 53
-    d2h = 4 * (2 * HORIZON * 9) + C_sizeof_info()
+    waits = torch.tensor([float(np.mean(wait_j)), float(np.mean(wait_p)), float(np.mean(roll_ms))], dtype=torch.float64, device="cuda")
+    waits_all = [torch.zeros_like(waits) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(waits_all, waits)
+    else:
+        waits_all = [waits]
+    # N > 1: the single-GPU command of the SAME workload (one shard's K, unsharded) on rank 0's GPU, so that the weak
+    # scaling of this workload can be read from this line alone (the default N = 1 line is another workload: c4)
+    n1_same = None
+    if world > 1:
+        if rank == 0:
+            solo, _, _, _ = build_planner(conf, 1, 0, local_rank, "none")
+            solo.set_stream(stream.cuda_stream)
+            for _ in range(args.warmup):
+                solo.command_resident()
+            torch.cuda.synchronize()
+            n_solo = min(args.steps, 50)
+            ev1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_solo)]
+            for i in range(n_solo):
+                if flush is not None:
+                    flush.fill_(i & 1)
+                ev1[i][0].record(stream)
+                solo.command_resident()
+                ev1[i][1].record(stream)
+            torch.cuda.synchronize()
+            ms1 = float(np.mean([a.elapsed_time(b) for a, b in ev1]))
+            n1_same = {"ms_per_step": ms1, "value": K * T / (ms1 * 1e-3), "steps": n_solo,
+                       "note": "same workload, one GPU, K = K_per_gpu unsharded, measured on rank 0 after the sharded run"}
+            solo.close()
+        barrier()
+    clocks = sampler.summary(t_timed0, t_timed1)
+    nf = 22 if env == "point_env" else 53
+    nu = 2 if env == "point_env" else 9
+    h2d = 4 * nf
+    d2h = 4 * (2 * T * nu) + C_sizeof_info()
 
     if rank == 0:
         peak, peak_src = peaks()
         r_ms = float(np.mean(roll_ms))
-        achieved = B_ROLLOUT * K_PER_GPU * HORIZON / (r_ms * 1e-3) / 1e9
+        b_roll = B_ROLLOUT[env]
+        achieved = b_roll * K * T / (r_ms * 1e-3) / 1e9
+        traffic, issue = ncu_numbers(name)
+        kernel = (f"k_rollout_team (panda_env, {lanes} lanes per sample)" if lanes > 1 else f"k_rollout<{env}> (thread per sample)")
         line = {
-            "metric": "sample-steps/sec (K x H per command)", "value": Kg * HORIZON / (ms_per_step * 1e-3),
+            "metric": "sample-steps/sec (K x H per command)", "value": Kg * T / (ms_per_step * 1e-3),
             "unit": "sample-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "K_global": Kg, "H": HORIZON, "noise": "philox4x32-10 in-kernel",
-                       "dt": 0.01, "substeps": 2, "solver_passes": 2, "link_sweeps": 4,
+            "ms_per_step": ms_per_step, "ms_per_step_median": ms_median, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": conf["workload"], "name": name, "K_global": Kg, "K_per_gpu": K, "H": T,
+                       "multi_modal": bool(conf["mm"]), "noise": "philox4x32-10 in-kernel",
+                       "dt": 0.05 if env == "point_env" else 0.01, "substeps": 2, "solver_passes": 2, "link_sweeps": 2,
                        "exchange": {"none": "single rank", "peer": "stores into peer HBM over NVLink from inside the rollout / "
                                     "weighted-sum kernels (no collective call)"}.get(exchange, exchange),
                        "l2": "not flushed" if flush is None else "flushed between steps (256 MiB fill outside the timed events)",
-                       "timing": "CUDA events per step on the launching stream, max over ranks, mean over steps"},
-            "e2e": {"value": Kg * HORIZON / e2e_s, "unit": "sample-steps/s", "h2d_bytes_per_step": h2d,
+                       "timing": "CUDA events per step on the launching stream, max over ranks per step; value from the mean over steps"},
+            "e2e": {"value": Kg * T / e2e_s, "unit": "sample-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
                     "api": "NativePlanner.set_state + command (m3p2i_set_state / m3p2i_command), host arrays"},
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": (f"k_rollout_team (panda_env, {lanes} lanes per sample)" if lanes > 1 else "k_rollout<panda_env> (thread per sample)"), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(), "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_ncu_rollout_team_summary.csv)",
-                         "algorithmic_bytes_per_launch": B_ROLLOUT * K_PER_GPU * HORIZON, "peak_source": peak_src,
-                         "bytes_per_sample_step": B_ROLLOUT, "kernel_ms": r_ms,
-                         "path_bytes_per_sample_step": B_PATH,
-                         "note": "issue/latency-bound, not HBM-bound: the 7.3 MB of outputs stay in the 126 MB L2 (DRAM traffic < algorithmic bytes); see DESIGN.md 5"},
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_unit": f"bytes per launch (ncu --set full, profiles/{NCU_SUMMARY.get(name, 'none for this workload')})",
+                         "algorithmic_bytes_per_launch": b_roll * K * T, "peak_source": peak_src,
+                         "bytes_per_sample_step": b_roll, "kernel_ms": r_ms, "path_bytes_per_sample_step": B_PATH[env],
+                         "issue_frac": None if issue is None else issue / 100.0,
+                         "issue_frac_source": "smsp__issue_active.avg.pct_of_peak_sustained_active of the same ncu capture: the "
+                                              "roofline that binds this kernel (instruction issue / dependent-instruction latency)",
+                         "note": "issue/latency-bound, not HBM-bound: the outputs stay in the 126 MB L2 (DRAM traffic < "
+                                 "algorithmic bytes); see DESIGN.md 5"},
         }
+        if n1_same is not None:
+            line["single_gpu_same_workload"] = n1_same
+            line["weak_scaling_efficiency_same_workload"] = (line["value"] / world) / n1_same["value"]
+        if world > 1:
+            w = torch.stack(waits_all).cpu().numpy()
+            line["peer_wait_ms"] = {"wait_costs_mean_over_ranks": float(w[:, 0].mean()), "wait_costs_max_rank": float(w[:, 0].max()),
+                                    "wait_partials_mean_over_ranks": float(w[:, 1].mean()), "wait_partials_max_rank": float(w[:, 1].max()),
+                                    "rollout_ms_per_rank": [float(x) for x in w[:, 2]],
+                                    "note": "device time (globaltimer) each rank spends at the two hand-overs of the exchange, "
+                                            "commands entered together after a host barrier: the wait for the costs is the skew of "
+                                            "the rollout kernels (different samples, different contact counts) plus the NVLink stores"}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            v, n, med = cpu_oracle_rate(cores, args.cpu_seconds)
-            line["cpu_baseline"] = {"value": v, "unit": "sample-steps/s", "cores": cores, "kind": "port",
-                                    "sample": f"{n} commands of K={K_PER_GPU}, H={HORIZON} (median {med * 1e3:.1f} ms), "
-                                              "oracle/ C port, OpenMP over samples"}
+            try:
+                import reference_rig as R
+                have_ref = R.reference_dir() is not None
+            except Exception:
+                have_ref = False
+            port_v, port_n, port_med = cpu_port_rate(conf, cores, 4.0)
+            if have_ref:
+                t1 = cpu_reference_python(conf, K, cores, 1, 0)[0][0]
+                n = int(max(2, min(40, args.cpu_seconds / max(t1, 1e-3))))
+                times, src = cpu_reference_python(conf, K, cores, n, 1)
+                v = K * T / float(np.median(times))
+                line["cpu_baseline"] = {"value": v, "unit": "sample-steps/s", "cores": cores, "kind": REF_KIND,
+                                        "sample": f"{n} commands of K={K}, H={T} (median {np.median(times) * 1e3:.1f} ms); " + REF_NOTE,
+                                        "port": {"value": port_v, "kind": "port", "sample": f"{port_n} commands, median {port_med * 1e3:.1f} ms: "
+                                                 "the whole path in C (oracle/, OpenMP over samples)"}}
+            else:
+                line["cpu_baseline"] = {"value": port_v, "unit": "sample-steps/s", "cores": cores, "kind": "port",
+                                        "sample": f"{port_n} commands of K={K}, H={T} (median {port_med * 1e3:.1f} ms), oracle/ C port, "
+                                                  "OpenMP over samples (baseline/_ref missing)"}
         print(json.dumps(line), flush=True)
     planner.close()
     if world > 1:

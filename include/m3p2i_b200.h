@@ -236,6 +236,9 @@ typedef struct M3P2ICommandInfo {
   int32_t beta_iters; /* iterations of the on-the-fly beta search (m3p2i.py:30-43), summed over sets */
   float rollout_ms;   /* device time of the fused rollout kernel alone (the roofline figure is computed from it) */
   int32_t rollout_lanes; /* lanes per sample of the rollout kernel this command used (1, 8 or 16) */
+  float peer_wait_ms[2]; /* sharded over peer memory: device time this rank spent waiting for [0] the discounted costs of
+                            all ranks (start of the softmin kernel: rollout skew between ranks + the NVLink stores) and
+                            [1] the partial sums of all ranks (end of the weighted-sum kernel); 0 when unsharded */
 } M3P2ICommandInfo;
 
 typedef struct M3P2IHandle_* m3p2i_handle;

@@ -250,8 +250,10 @@ __global__ void __launch_bounds__(kStatsBlock) k_stats(const UpdateCfg u, const 
   const int Kg = u.Kg, half = Kg / 2;
   const float* J = b.J_global;
   // sharded over peer memory: J_global is the local mailbox; every rank's slice has landed once its flag is up
-  if (b.peer.n) wait_flags(b.peer.jflag_local, b.peer.n, b.peer.epoch, b.peer.timeout_ms, b.peer.error);
   Stats* S = b.stats;
+  if (b.peer.n) wait_flags(b.peer.jflag_local, b.peer.n, b.peer.epoch, b.peer.timeout_ms, b.peer.error,
+                           blockIdx.x == 0 ? &S->peer_wait_ms[0] : nullptr);
+  else if (blockIdx.x == 0 && threadIdx.x == 0) { S->peer_wait_ms[0] = 0.0f; S->peer_wait_ms[1] = 0.0f; }
   // multi-modal: the three weight sets (all / first half / second half) are independent searches: one CTA each
   const int s = blockIdx.x;
   int iters = 0;
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(kSumBlock) k_wsum(const UpdateCfg u, const Upd
     if (threadIdx.x == 0)
       for (int r = 0; r < p.n; ++r) *(volatile unsigned*)(p.pflag[r] + p.rank) = p.epoch;
     // ... and the n boxes of the own mailbox are added in rank order (the same bits on every rank)
-    wait_flags(p.pflag_local, p.n, p.epoch, p.timeout_ms, p.error);
+    wait_flags(p.pflag_local, p.n, p.epoch, p.timeout_ms, p.error, &b.stats->peer_wait_ms[1]);
     for (int i = threadIdx.x; i < NP; i += kSumBlock) {
       float a = 0.0f;
       for (int r = 0; r < p.n; ++r) a += __ldcg(p.part_local + (size_t)r * p.np + i);
@@ -472,6 +474,7 @@ DEV void finish_body(const UpdateCfg& u, const UpdateBufs& b, float* smean /* sh
     in->weight_push = S->weight_push; in->weight_pull = S->weight_pull;
     in->mean_cost_sum = mean_cost;
     in->beta_iters = S->beta_iters;
+    in->peer_wait_ms[0] = S->peer_wait_ms[0]; in->peer_wait_ms[1] = S->peer_wait_ms[1];
   }
 }
 

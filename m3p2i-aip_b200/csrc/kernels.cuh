@@ -21,6 +21,7 @@ struct Stats {
   int best_idx[3];      // global index of the best sample of each set
   float weight_push, weight_pull;
   int beta_iters;
+  float peer_wait_ms[2];   // device time spent in the two waits of the peer-memory exchange (0 when unsharded)
 };
 
 struct UpdateBufs {

@@ -132,7 +132,10 @@ DEV unsigned long long global_ns() {
   return 0ull;
 #endif
 }
-DEV void wait_flags(const unsigned* flags, int n, unsigned epoch, unsigned timeout_ms, unsigned* error) {
+// Returns (in every thread) nothing; thread 0 gets the time the CTA spent here in *waited_ms when that is not null.
+DEV void wait_flags(const unsigned* flags, int n, unsigned epoch, unsigned timeout_ms, unsigned* error,
+                    float* waited_ms = nullptr) {
+  const unsigned long long t_in = threadIdx.x == 0 ? global_ns() : 0ull;
   if ((int)threadIdx.x < n) {
     const volatile unsigned* f = flags + threadIdx.x;
     const unsigned long long t0 = global_ns(), limit = (unsigned long long)timeout_ms * 1000000ull;
@@ -144,6 +147,7 @@ DEV void wait_flags(const unsigned* flags, int n, unsigned epoch, unsigned timeo
   }
   __threadfence_system();
   __syncthreads();
+  if (threadIdx.x == 0 && waited_ms) *waited_ms = (float)(global_ns() - t_in) * 1e-6f;
 }
 
 }  // namespace m3

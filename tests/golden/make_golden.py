@@ -33,81 +33,14 @@ import oracle_py as O  # noqa: E402
 from m3p2i_b200 import scene as S  # noqa: E402
 from m3p2i_aip.utils.isaacgym_utils import isaacgym_wrapper as our_wrapper  # noqa: E402  (this repo's facade)
 
+from reference_rig import Tamp, import_reference as _import_reference  # noqa: E402  (oracle/reference_rig.py)
+
 REF_SRC = "/root/reference/src"
 
 
 def import_reference():
-    """Reference modules under the private name space `ref_m3p2i_aip` would break their absolute imports, so the
-    facade of this repo is imported first (above) and the reference package is then loaded under its own name from
-    a separate module table."""
-    saved = {k: v for k, v in sys.modules.items() if k == "m3p2i_aip" or k.startswith("m3p2i_aip.")}
-    for k in saved:
-        del sys.modules[k]
-    gh = types.ModuleType("ghalton")
-    gh.EA_PERMS = []
-    gh.GeneralizedHalton = object
-    ig = types.ModuleType("isaacgym")
-    gymapi = types.ModuleType("isaacgym.gymapi")
-    gymapi.SimParams = type("SimParams", (), {})
-    gymtorch = types.ModuleType("isaacgym.gymtorch")
-    ig.gymapi, ig.gymtorch = gymapi, gymtorch
-    sys.modules.update({"ghalton": gh, "isaacgym": ig, "isaacgym.gymapi": gymapi, "isaacgym.gymtorch": gymtorch})
-    sys.path.insert(0, REF_SRC)
-    try:
-        from m3p2i_aip.planners.motion_planner import m3p2i as ref_m3p2i
-        from m3p2i_aip.planners.motion_planner import cost_functions as ref_cost
-        from m3p2i_aip.utils import skill_utils as ref_skill
-    finally:
-        sys.path.remove(REF_SRC)
-    assert ref_m3p2i.__file__.startswith(REF_SRC), ref_m3p2i.__file__
-
-    class _TorchCPU:
-        def __getattr__(self, name):
-            return getattr(torch, name)
-
-        @staticmethod
-        def zeros(*a, **kw):
-            kw.pop("device", None)
-            return torch.zeros(*a, **kw)
-    ref_skill.torch = _TorchCPU()
-    ref = {k: v for k, v in sys.modules.items() if k == "m3p2i_aip" or k.startswith("m3p2i_aip.")}
-    for k in ref:
-        del sys.modules[k]
-    sys.modules.update(saved)
-    return ref_m3p2i, ref_cost
-
-
-class Tamp:
-    """scripts/reactive_tamp.py:21-73 without zerorpc/hydra and with a fixed task (no task planner)."""
-
-    def __init__(self, cfg, ref_m3p2i, ref_cost):
-        self.sim = our_wrapper.IsaacGymWrapper(cfg.isaacgym, cfg.env_type, num_envs=cfg.mppi.num_samples, viewer=False,
-                                               device="cpu", cube_on_shelf=cfg.cube_on_shelf,
-                                               backend_factory=O.Oracle.for_sim)
-        self.cfg = cfg
-        self.objective = ref_cost.Objective(cfg)
-        self.motion_planner = ref_m3p2i.M3P2I(cfg, dynamics=self.dynamics, running_cost=self.running_cost)
-
-    def dynamics(self, _, u, t=None):
-        self.sim.set_dof_velocity_target_tensor(u)
-        self.sim.step()
-        states = torch.stack([self.sim.robot_pos[:, 0], self.sim.robot_vel[:, 0], self.sim.robot_pos[:, 1],
-                              self.sim.robot_vel[:, 1]], dim=1)
-        return states, u
-
-    def running_cost(self, _):
-        return self.objective.compute_cost(self.sim)
-
-    def run_tamp(self, dof_state, root_state, task, goal, extra_step):
-        self.sim._dof_state[:] = dof_state
-        self.sim._root_state[:] = root_state
-        self.sim.set_dof_state_tensor(self.sim._dof_state)
-        self.sim.set_actor_root_state_tensor(self.sim._root_state)
-        if extra_step:
-            self.sim.step()  # PLANNER_AIF_PANDA.update_plan, task_planner.py:79
-        self.motion_planner.update_gripper_command(task)
-        self.objective.update_objective(task, goal)
-        return self.motion_planner.command(self.sim._dof_state[0])
+    """The goldens are generated from the reference checkout itself."""
+    return _import_reference(REF_SRC)
 
 
 CASES = [

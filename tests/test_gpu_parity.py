@@ -278,6 +278,9 @@ def test_team_and_thread_kernels_agree(task, mm, shelf):
             b.set_objective(task, goal, {"pick": "close", "reach": "open"}[task])
         outs = []
         for i in range(3):
+            # every tick starts from the SAME planner state (the oracle's): what is compared is one command on equal
+            # inputs; the drift of two closed loops over several ticks is not a property of a kernel
+            n.set_planner_state(o.get_planner_state())
             a_n, _, _ = n.command()
             a_o, _, _ = o.command()
             st_n, ch_n = n.read_buffer(A.BUF_STATES), n.read_buffer(A.BUF_COST_HORIZON)

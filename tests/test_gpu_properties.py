@@ -191,3 +191,43 @@ def test_errors_are_loud():
     with pytest.raises(native.NativeError, match="nu"):
         native.NativePlanner(bad, S.build_point_scene())
     n.close()
+
+
+@pytest.mark.parametrize("offset", [0, 16384])
+def test_c5_shard_matches_oracle(offset):
+    """BASELINE configs[4] as stated: config_panda multi_modal=True cube_on_shelf=True, K_global = 32768, H = 32, sharded
+    over 8 GPUs. One GPU's shard (K_local = 4096) at the two interesting places -- the shard that owns global row 0 and
+    the one that starts at the mode boundary K/2 = 16384 (it owns the row whose cube axis every second-mode cost reads,
+    skill_utils.py:275-279, and must replay row 0 of another shard, cost_functions.py:98) -- against the oracle
+    evaluating the same shard with the same Philox counters: actions, per-step costs, discounted costs. A second tick
+    follows from planner sequences that are no longer zero (both shards must rebuild the foreign rows from them)."""
+    O.set_threads(8)
+    Kg, Kl, T = 32768, 4096, 32
+    cfg = S.make_cfg("panda_env", "reach", None, Kg, T, multi_modal=True, cube_on_shelf=True)
+    actors = S.default_actors("panda_env")
+    dof, root = S.initial_dof_state(actors).copy(), S.initial_root_state(actors, True).copy()
+    root[S.actor_index(actors, "cubeB"), 2] -= 0.0095
+    pair = []
+    for cls in (O.Oracle, native.NativePlanner):
+        b = make_backend(cls, cfg, noise_mode=A.NOISE_PHILOX, seed=5, K_local=Kl, offset=offset)
+        b.set_state(dof, root)
+        b.set_objective("reach", np.zeros(7, np.float32), "open")
+        pair.append(b)
+    o, n = pair
+    rng = np.random.default_rng(3)
+    for tick in range(2):
+        if tick == 1:
+            st = o.get_planner_state()   # non-trivial means / best rows for both modes, identical on both backends
+            for key in ("mean_action", "mean_action_1", "mean_action_2", "best_traj_1", "best_traj_2"):
+                arr = getattr(st, key)
+                for i, v in enumerate(rng.uniform(-0.5, 0.5, T * 9).astype(np.float32)):
+                    arr[i] = float(v)
+            o.set_planner_state(st)
+            n.set_planner_state(st)
+        J_o, J_n = o.phase_rollout(), n.phase_rollout()
+        assert_close(n.read_buffer(A.BUF_ACTIONS), o.read_buffer(A.BUF_ACTIONS), 1e-4, 1e-4, f"c5 shard@{offset}[{tick}] actions")
+        assert_close(n.read_buffer(A.BUF_COST_HORIZON), o.read_buffer(A.BUF_COST_HORIZON), 1e-3, 1e-3,
+                     f"c5 shard@{offset}[{tick}] cost_horizon", 0.005)
+        assert_close(J_n, J_o, 1e-3, 1e-3, f"c5 shard@{offset}[{tick}] discounted costs", 0.005)
+    o.close()
+    n.close()
