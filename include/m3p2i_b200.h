@@ -112,7 +112,9 @@ typedef struct M3P2IConfig {
   int32_t solver_passes;       /* contact solver sweeps per substep (our integrator; default 2) */
   int32_t lanes_per_sample;    /* rollout kernel shape: 0 = library chooses, 1 = one thread per sample,
                                   8 / 16 = lane-cooperative team of that many lanes per sample (panda_env) */
-  int32_t reserved_i[3];
+  int32_t update_cov;          /* cfg.mppi.update_cov (mppi.py:43,508-516): adapt the per-dimension noise variance from the
+                                  weighted second moment of the samples (single-mode only, as in the reference) */
+  int32_t reserved_i[2];
   float dt;                    /* cfg.isaacgym.dt */
   float gamma;                 /* cfg.mppi.rollout_var_discount (mppi.py:181) */
   float step_size_mean;        /* 0.98 (mppi.py:178) */
@@ -220,6 +222,9 @@ typedef struct M3P2IPlannerState {
   float best_traj_1[M3P2I_MAX_HORIZON * M3P2I_MAX_NU];
   float best_traj_2[M3P2I_MAX_HORIZON * M3P2I_MAX_NU];
   double beta;                /* single-mode inverse temperature (adapted across calls for panda_env) */
+  float cov_action[M3P2I_MAX_NU]; /* per-dimension noise variance (mppi.py:175; changes only with update_cov); the
+                                  noise scale of the next command is its square root (scale_tril, mppi.py:176,516) */
+  float reserved;
 } M3P2IPlannerState;
 
 /* Scalars produced by one command() */
@@ -332,7 +337,8 @@ int m3p2i_sim_read(m3p2i_handle h, float* dof_state, float* root_state, float* l
                    float* contact_force);
 
 /* ---- multi-GPU: K sharded over ranks, one process per GPU ---- */
-/* Number of floats in the packed partial-sum buffer exchanged by the second collective. */
+/* Number of floats in the packed partial-sum buffer exchanged by the second collective:
+ * [sum w a | sum w1 a | sum w2 a | best row x3] (6 T nu), sum of the undiscounted costs (1), sum w a^2 (T nu). */
 int m3p2i_partials_len(m3p2i_handle h);
 /* Host-staged three-phase tick (any transport, e.g. torch.distributed gloo); the NCCL path of
  * m3p2i_command runs the same three phases with the two collectives enqueued on the handle's stream.

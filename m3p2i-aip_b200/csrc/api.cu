@@ -262,7 +262,8 @@ RolloutBufs make_rbufs(const H* h) {
   RolloutBufs b;
   b.noise = h->have_noise ? h->noise.p : nullptr;
   b.noise_row0 = h->have_row0 ? h->noise_row0.p : nullptr;
-  b.seq = h->seq.p; b.actions_in = nullptr; b.base = h->base.p; b.env = h->env.p; b.vel_target = h->vel_target.p;
+  b.seq = h->seq.p; b.actions_in = nullptr; b.base = h->base.p;
+  b.sigma_dev = h->cfg.update_cov ? h->stats.p->sigma : nullptr; b.env = h->env.p; b.vel_target = h->vel_target.p;
   b.actions = h->actions.p; b.states = h->states.p; b.cost_h = h->cost_h.p; b.J = h->J.p; b.cost_sum = h->cost_sum.p;
   b.refs = nullptr;
   b.ref_flags = h->ref_flags.p;
@@ -277,7 +278,7 @@ struct MailboxLayout {
 MailboxLayout mailbox_layout(const H* h) {
   MailboxLayout m;
   const size_t Kg = ((size_t)h->cfg.num_samples_global + 31) / 32 * 32;
-  m.np = (6 * (size_t)h->cfg.horizon * h->cfg.nu + 1 + 31) / 32 * 32;
+  m.np = (7 * (size_t)h->cfg.horizon * h->cfg.nu + 1 + 31) / 32 * 32;
   m.off_part = Kg;
   m.off_jflag = m.off_part + kMaxPeers * m.np;
   m.off_pflag = m.off_jflag + 32;
@@ -317,6 +318,7 @@ UpdateCfg make_ucfg(const H* h, int shift) {
   u.multi_modal = c.multi_modal; u.env_type = c.env_type; u.filter_u = c.filter_u && h->have_filt; u.shift = shift;
   u.gamma = c.gamma; u.step_size_mean = c.step_size_mean;
   u.fuse_finish = 0;
+  u.update_cov = c.update_cov && !c.multi_modal;
   return u;
 }
 
@@ -418,7 +420,7 @@ int gather_J(H* h) {
 
 int reduce_partials(H* h) {
   if (h->nranks == 1 || !h->comm) return 0;
-  const size_t n = 6 * (size_t)h->cfg.horizon * h->cfg.nu + 1;
+  const size_t n = 7 * (size_t)h->cfg.horizon * h->cfg.nu + 1;
   ncclResult_t r = g_nccl.AllReduce(h->partials.p, h->partials.p, n, ncclFloat, ncclSum, h->comm, h->stream);
   if (r != ncclSuccess) return fail(M3P2I_ERR_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
   return 0;
@@ -561,7 +563,7 @@ int m3p2i_create(const M3P2IConfig* cfg, int device, m3p2i_handle* out) {
   if (e == cudaSuccess) e = h->cost_sum.alloc(K);
   if (e == cudaSuccess) e = h->J_global.alloc(Kg);
   if (e == cudaSuccess) e = h->weights.alloc(3 * Kg);
-  if (e == cudaSuccess) e = h->partials.alloc(6 * TN + 1);
+  if (e == cudaSuccess) e = h->partials.alloc(7 * TN + 1);
   if (e == cudaSuccess) e = h->cost_total.alloc(K);
   if (e == cudaSuccess) e = h->result.alloc(2 * TN);
   if (e == cudaSuccess) e = h->refs.alloc(T);
@@ -574,6 +576,7 @@ int m3p2i_create(const M3P2IConfig* cfg, int device, m3p2i_handle* out) {
     Stats s;
     memset(&s, 0, sizeof(s));
     s.beta = 1.0;
+    for (int d = 0; d < kMaxNu; ++d) { s.sigma[d] = c.sigma[d]; s.cov[d] = c.sigma[d] * c.sigma[d]; }   // mppi.py:175-176
     e = cudaMemcpy(h->stats.p, &s, sizeof(s), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);   // pageable H2D may still be in flight
   }
@@ -752,6 +755,7 @@ int m3p2i_get_planner_state(m3p2i_handle h, M3P2IPlannerState* out) {
                            out->best_traj_2};
   for (int i = 0; i < SEQ_COUNT; ++i) memcpy(dst[i], tmp.data() + i * TN, sizeof(float) * TN);
   out->beta = s.beta;
+  for (int d = 0; d < kMaxNu; ++d) out->cov_action[d] = s.cov[d];
   return 0;
 }
 
@@ -764,6 +768,14 @@ int m3p2i_set_planner_state(m3p2i_handle h, const M3P2IPlannerState* in) {
   for (int i = 0; i < SEQ_COUNT; ++i) memcpy(tmp.data() + i * TN, src[i], sizeof(float) * TN);
   CK(cudaMemcpyAsync(h->seq.p, tmp.data(), sizeof(float) * tmp.size(), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(&h->stats.p->beta, &in->beta, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  bool have_cov = false;
+  for (int d = 0; d < h->cfg.nu; ++d) have_cov = have_cov || in->cov_action[d] > 0.0f;
+  float cs[2 * kMaxNu];
+  if (have_cov) {   // a state captured before cov_action existed (all zero) keeps the current variance
+    for (int d = 0; d < kMaxNu; ++d) { cs[d] = in->cov_action[d]; cs[kMaxNu + d] = sqrtf(fmaxf(in->cov_action[d], 0.0f)); }
+    CK(cudaMemcpyAsync(h->stats.p->cov, cs, sizeof(float) * kMaxNu, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->stats.p->sigma, cs + kMaxNu, sizeof(float) * kMaxNu, cudaMemcpyHostToDevice, h->stream));
+  }
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -1085,7 +1097,7 @@ int m3p2i_sim_read(m3p2i_handle h, float* dof, float* root, float* link, float* 
 }
 
 // ---------------------------------------------------------------------------------------------- multi-GPU
-int m3p2i_partials_len(m3p2i_handle h) { return h ? 6 * h->cfg.horizon * h->cfg.nu + 1 : -1; }
+int m3p2i_partials_len(m3p2i_handle h) { return h ? 7 * h->cfg.horizon * h->cfg.nu + 1 : -1; }
 
 int m3p2i_phase_rollout(m3p2i_handle h, float* out_J_local) {
   int rc = check_ready(h);
@@ -1102,7 +1114,7 @@ int m3p2i_phase_rollout(m3p2i_handle h, float* out_J_local) {
 
 int m3p2i_phase_partials(m3p2i_handle h, const float* J_global, float* out_partials) {
   if (!h || !J_global || !out_partials) return fail(M3P2I_ERR_ARG, "null argument");
-  const size_t n = 6 * (size_t)h->cfg.horizon * h->cfg.nu + 1;
+  const size_t n = 7 * (size_t)h->cfg.horizon * h->cfg.nu + 1;
   CK(cudaMemcpyAsync(h->J_global.p, J_global, sizeof(float) * h->cfg.num_samples_global, cudaMemcpyHostToDevice, h->stream));
   int launches = 0, rc;
   if ((rc = run_update(h, 1, &launches))) return rc;
@@ -1115,7 +1127,7 @@ int m3p2i_phase_partials(m3p2i_handle h, const float* J_global, float* out_parti
 int m3p2i_phase_finish(m3p2i_handle h, const float* partials_sum, float* out_action, float* out_cost_total,
                        M3P2ICommandInfo* info) {
   if (!h || !partials_sum) return fail(M3P2I_ERR_ARG, "null argument");
-  const size_t n = 6 * (size_t)h->cfg.horizon * h->cfg.nu + 1;
+  const size_t n = 7 * (size_t)h->cfg.horizon * h->cfg.nu + 1;
   CK(cudaMemcpyAsync(h->partials.p, partials_sum, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
   int launches = 0, rc;
   if ((rc = run_finish(h, 1, &launches))) return rc;

@@ -119,6 +119,7 @@ struct RolloutBufs {
   const float* noise_row0; // [T][nu] noise of GLOBAL sample 0 for shards that do not own it, or nullptr
   const float* seq;        // [SEQ_COUNT][T*nu] planner sequences (un-shifted; the kernel reads them shifted)
   const float* actions_in; // [T][nu][K] open-loop actions or nullptr
+  const float* sigma_dev;  // [nu] adapted noise scale (update_cov) or nullptr: use RolloutCfg::sigma
   const float* base;       // one env, field-major (broadcast start state)
   float* env;              // [fields][K] persistent envs
   float* vel_target;       // [nu][K]

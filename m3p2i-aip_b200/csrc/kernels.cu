@@ -359,10 +359,11 @@ __global__ void __launch_bounds__(kSumBlock) k_wsum(const UpdateCfg u, const Upd
   const float* w0 = b.weights + u.offset;
   const float* w1 = b.weights + (size_t)Kg + u.offset;
   const float* w2 = b.weights + 2 * (size_t)Kg + u.offset;
-  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, sq = 0.0f;
   for (int k = threadIdx.x; k < K; k += kSumBlock) {
     const float a = plane[k];
     s0 += w0[k] * a;
+    sq += w0[k] * a * a;   // second moment for the covariance update (mppi.py:508-516)
     if (u.multi_modal) {
       if (u.offset + k < half) s1 += w1[k] * a;
       else s2 += w2[k] * a;
@@ -370,8 +371,9 @@ __global__ void __launch_bounds__(kSumBlock) k_wsum(const UpdateCfg u, const Upd
   }
   s0 = block_sum<kSumBlock>(s0, sh);
   if (u.multi_modal) { s1 = block_sum<kSumBlock>(s1, sh); s2 = block_sum<kSumBlock>(s2, sh); }
+  if (u.update_cov) sq = block_sum<kSumBlock>(sq, sh);
   if (threadIdx.x == 0) {
-    b.partials[j] = s0; b.partials[TN + j] = s1; b.partials[2 * TN + j] = s2;
+    b.partials[j] = s0; b.partials[TN + j] = s1; b.partials[2 * TN + j] = s2; b.partials[6 * TN + 1 + j] = sq;
     const int nsets = u.multi_modal ? 3 : 1;
     for (int s = 0; s < 3; ++s) {
       float row = 0.0f;
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(kSumBlock) k_wsum(const UpdateCfg u, const Upd
   if (b.peer.n) {
     // all-reduce over peer memory: this rank's packed partial sums go into box [rank] of every mailbox ...
     const PeerReduce& p = b.peer;
-    const int NP = 6 * TN + 1;
+    const int NP = 7 * TN + 1;
     const volatile float* mine = b.partials;
     for (int i = threadIdx.x; i < NP; i += kSumBlock) {
       const float v = mine[i];
@@ -460,6 +462,24 @@ DEV void finish_body(const UpdateCfg& u, const UpdateBufs& b, float* smean /* sh
     }
     b.result[i] = out;
     b.result[TN + i] = smean[i];
+  }
+  if (u.update_cov && !u.multi_modal) {
+    // mppi.py:505-516: delta = actions - NEW mean; cov_update_d = mean_t sum_k w_k delta_ktd^2 from the moments
+    // sum w a^2, sum w a (sum w = 1); step_size_cov = 0.7, kappa = 0.005 (mppi.py:202-203)
+    __syncthreads();
+    if ((int)threadIdx.x < nu) {
+      const int d = threadIdx.x;
+      double acc = 0.0;
+      for (int t = 0; t < T; ++t) {
+        const double m = smean[t * nu + d];
+        acc += (double)part[6 * TN + 1 + t * nu + d] - 2.0 * m * (double)part[t * nu + d] + m * m;
+      }
+      Stats* S = b.stats;
+      float cov = (1.0f - 0.7f) * S->cov[d] + 0.7f * (float)(acc / (double)T);
+      cov += 0.005f;
+      S->cov[d] = cov;
+      S->sigma[d] = sqrtf(cov);
+    }
   }
   const float mean_cost = part[6 * TN] / (float)u.Kg;
   for (int k = threadIdx.x; k < u.K; k += kSumBlock) b.cost_total[k] = b.cost_sum[k] + mean_cost;

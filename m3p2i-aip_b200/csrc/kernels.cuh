@@ -7,6 +7,7 @@ namespace m3 {
 struct UpdateCfg {
   int K, T, nu, Kg, offset, multi_modal, env_type, filter_u, shift;
   int fuse_finish;   // k_wsum's last CTA also runs the finish step (no exchange between them: single rank)
+  int update_cov;    // adapt the per-dimension noise variance (mppi.py:508-516; single-mode only)
   float gamma, step_size_mean;
 };
 
@@ -22,6 +23,8 @@ struct Stats {
   float weight_push, weight_pull;
   int beta_iters;
   float peer_wait_ms[2];   // device time spent in the two waits of the peer-memory exchange (0 when unsharded)
+  float cov[kMaxNu];       // per-dimension noise variance cov_action (mppi.py:175,514-515) and its square root, the
+  float sigma[kMaxNu];     //   noise scale scale_tril of the next command (mppi.py:176,516); used when update_cov
 };
 
 struct UpdateBufs {
@@ -30,7 +33,7 @@ struct UpdateBufs {
   Stats* stats;
   const float* actions;    // [T][nu][K]
   const float* cost_sum;   // [K]
-  float* partials;         // [6*T*nu + 1]
+  float* partials;         // [7*T*nu + 1]: sums / best rows (6 T nu), sum of costs, sum w a^2 (T nu)
   float* seq;              // [SEQ_COUNT][T*nu]
   const float* filt;       // [T][T] or nullptr
   float* cost_total;       // [K]

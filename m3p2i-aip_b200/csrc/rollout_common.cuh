@@ -18,7 +18,7 @@ DEV void perturb_action(const RolloutCfg& c, const RolloutBufs& b, int kg, int t
 #pragma unroll
   for (int d = 0; d < NU; ++d) {
     const float delta = kg == c.Kg - 1 ? 0.0f : delta_in[d];
-    float v = mean[d] + delta * c.sigma[d];
+    float v = mean[d] + delta * (b.sigma_dev ? b.sigma_dev[d] : c.sigma[d]);
     v = fmaxf(fminf(v, c.u_max[d]), c.u_min[d]);
     if (c.multi_modal) {
       if (kg == 0) v = b.seq[SEQ_BEST1 * TN + ts * NU + d];
@@ -60,7 +60,7 @@ DEV void sample_action(const RolloutCfg& c, const RolloutBufs& b, int kg, int kl
         delta = b.noise_row0 ? b.noise_row0[t * NU + d] : 0.0f;
       }
       if (kg == c.Kg - 1) delta = 0.0f;  // delta[-1] = 0: the mean itself is always a sample (mppi.py:392)
-      float v = mean[d] + delta * c.sigma[d];
+      float v = mean[d] + delta * (b.sigma_dev ? b.sigma_dev[d] : c.sigma[d]);
       v = fmaxf(fminf(v, c.u_max[d]), c.u_min[d]);
       if (c.multi_modal) {
         if (kg == 0) v = b.seq[SEQ_BEST1 * TN + ts * NU + d];

@@ -70,10 +70,9 @@ class MPPI():
         self.sampling_method = getattr(m, "sampling_method", "halton")
         if self.sampling_method not in ("halton", "random", "philox", "philox-spline"):
             raise ValueError(f"unknown sampling_method {self.sampling_method!r}")
-        # branches of the reference that no shipped YAML enables and this planner does not implement: say so instead
-        # of silently planning with a fixed covariance (mppi.py:43,508-516)
-        if bool(getattr(m, "update_cov", False)):
-            raise NotImplementedError("mppi.update_cov=True (covariance adaptation, mppi.py:508-516) is not implemented")
+        # covariance adaptation (mppi.py:43,508-516) runs in the update kernel; like the reference it only exists on the
+        # single-mode path (M3P2I._update_multi_modal_distribution has no covariance branch)
+        self.update_cov = bool(getattr(m, "update_cov", False))
         self.K = int(m.num_samples)
         self.half_K = int(self.K / 2)
         self.T = int(m.horizon)
@@ -299,6 +298,16 @@ class MPPI():
     @property
     def beta(self):
         return self.backend.get_planner_state().beta
+
+    @property
+    def cov_action(self):
+        """per-dimension noise variance (mppi.py:175,514-515); constant unless update_cov"""
+        st = self.backend.get_planner_state()
+        return torch.tensor([st.cov_action[d] for d in range(self.nu)], dtype=torch.float32)
+
+    @property
+    def scale_tril(self):
+        return torch.sqrt(self.cov_action)
 
     @property
     def weights(self):

@@ -32,7 +32,7 @@ class Config(C.Structure):
         ("env_type", i32), ("num_samples", i32), ("horizon", i32), ("nu", i32), ("multi_modal", i32),
         ("sample_null_action", i32), ("filter_u", i32), ("noise_mode", i32), ("num_samples_global", i32),
         ("sample_offset", i32), ("substeps", i32), ("solver_passes", i32), ("lanes_per_sample", i32),
-        ("reserved_i", i32 * 3),
+        ("update_cov", i32), ("reserved_i", i32 * 2),
         ("dt", f32), ("gamma", f32), ("step_size_mean", f32), ("u_scale", f32), ("kp_suction", f32),
         ("pre_height_diff", f32), ("tilt_cos_theta", f32), ("reserved_f", f32),
         ("u_min", f32 * MAX_NU), ("u_max", f32 * MAX_NU), ("sigma", f32 * MAX_NU),
@@ -76,7 +76,7 @@ class PlannerState(C.Structure):
         ("mean_action", f32 * (MAX_HORIZON * MAX_NU)), ("mean_action_1", f32 * (MAX_HORIZON * MAX_NU)),
         ("mean_action_2", f32 * (MAX_HORIZON * MAX_NU)), ("best_traj", f32 * (MAX_HORIZON * MAX_NU)),
         ("best_traj_1", f32 * (MAX_HORIZON * MAX_NU)), ("best_traj_2", f32 * (MAX_HORIZON * MAX_NU)),
-        ("beta", C.c_double),
+        ("beta", C.c_double), ("cov_action", f32 * MAX_NU), ("reserved", f32),
     ]
 
 

@@ -278,6 +278,7 @@ def build_config(cfg, num_samples_local=None, sample_offset=0, noise_mode=A.NOIS
     c.sample_null_action = int(bool(getattr(m, "sample_null_action", False)))
     c.filter_u = int(bool(getattr(m, "filter_u", False)))
     c.noise_mode = noise_mode
+    c.update_cov = int(bool(getattr(m, "update_cov", False)))
     ig = getattr(cfg, "isaacgym", None)
     c.substeps = int(getattr(ig, "substeps", 2)) if ig is not None else 2
     c.solver_passes = 2

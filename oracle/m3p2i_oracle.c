@@ -124,6 +124,7 @@ Oracle* orc_create(const M3P2IConfig* cfg) {
   o->weights = (float*)calloc(3 * Kg, 4);
   o->vel_target = (float*)calloc(K * nu, 4);
   o->st.beta = 1.0;
+  for (int d = 0; d < M3P2I_MAX_NU; ++d) o->st.cov_action[d] = cfg->sigma[d] * cfg->sigma[d]; /* mppi.py:175 */
   o->task = cfg->env_type == M3P2I_ENV_POINT ? M3P2I_TASK_NAVIGATION : M3P2I_TASK_REACH;
   return o;
 }
@@ -297,7 +298,8 @@ static void o_perturbed_action(const Oracle* o, int k, float* a) {
     for (int d = 0; d < nu; ++d) {
       float delta = o_noise(o, k, t, d);
       if (kg == Kg - 1) delta = 0.0f; /* delta[-1] = Z_seq, mppi.py:392 */
-      float scaled = delta * c->sigma[d];
+      /* scale_tril = sqrt(cov_action) (mppi.py:176,394,516): the configured sigma unless update_cov adapts it */
+      float scaled = delta * (c->update_cov ? sqrtf(o->st.cov_action[d]) : c->sigma[d]);
       const float* mean = c->multi_modal ? (kg < half ? o->st.mean_action_1 : o->st.mean_action_2) : o->st.mean_action;
       float v = mean[t * nu + d] + scaled;
       v = fmaxf(fminf(v, c->u_max[d]), c->u_min[d]); /* scale_ctrl clamp, mppi_utils.py:36 */
@@ -433,20 +435,20 @@ static void o_compute_stats(Oracle* o) {
   }
 }
 
-int orc_partials_len(Oracle* o) { return 6 * o->cfg.horizon * o->cfg.nu + 1; }
+int orc_partials_len(Oracle* o) { return 7 * o->cfg.horizon * o->cfg.nu + 1; }
 
 /* Phase 3: this shard's weighted action sums, its best-trajectory rows, its sum of undiscounted costs */
 static void o_compute_partials(Oracle* o, float* part) {
   const M3P2IConfig* c = &o->cfg;
   const int K = c->num_samples, T = c->horizon, nu = c->nu, Kg = c->num_samples_global, half = Kg / 2;
   const int TN = T * nu;
-  memset(part, 0, sizeof(float) * (6 * TN + 1));
+  memset(part, 0, sizeof(float) * (7 * TN + 1));
   int nsets = c->multi_modal ? 3 : 1;
   for (int k = 0; k < K; ++k) {
     int kg = c->sample_offset + k;
     const float* a = o->actions + (size_t)k * TN;
     float w0 = o->weights[kg];
-    for (int i = 0; i < TN; ++i) part[i] += w0 * a[i];
+    for (int i = 0; i < TN; ++i) { part[i] += w0 * a[i]; part[6 * TN + 1 + i] += w0 * a[i] * a[i]; }
     if (c->multi_modal) {
       int s = kg < half ? 1 : 2;
       float ws = o->weights[(size_t)s * Kg + kg];
@@ -475,6 +477,20 @@ static void o_finish(Oracle* o, const float* part, float* out_action, float* out
     }
   } else {
     for (int i = 0; i < TN; ++i) o->st.best_traj[i] = part[3 * TN + i];
+    if (c->update_cov) {
+      /* mppi.py:505-516: delta = actions - NEW mean; cov_update_d = mean_t sum_k w_k delta_ktd^2, from the moments
+       * sum w a^2, sum w a and sum w = 1; step_size_cov = 0.7, kappa = 0.005 (mppi.py:202-203) */
+      for (int d = 0; d < nu; ++d) {
+        double acc = 0.0;
+        for (int t = 0; t < T; ++t) {
+          const double m = o->st.mean_action[t * nu + d];
+          acc += (double)part[6 * TN + 1 + t * nu + d] - 2.0 * m * (double)part[t * nu + d] + m * m;
+        }
+        const float cov_update = (float)(acc / (double)T);
+        o->st.cov_action[d] = (1.0f - 0.7f) * o->st.cov_action[d] + 0.7f * cov_update;
+        o->st.cov_action[d] += 0.005f;
+      }
+    }
     if (c->env_type == M3P2I_ENV_PANDA) {
       if (o->info.eta[0] > 20.0f) o->st.beta = o->st.beta * 0.9;
       else if (o->info.eta[0] < 10.0f) o->st.beta = o->st.beta * 1.2;

@@ -164,6 +164,44 @@ def test_update_only_matches_oracle(env, K, T, mm):
     n.close()
 
 
+@pytest.mark.parametrize("env,K,T", [("point_env", 512, 20), ("panda_env", 4096, 32)])
+def test_update_cov_matches_oracle(env, K, T):
+    """mppi.update_cov (mppi.py:508-516) in the update kernels: the variance adapted from the weighted second moment
+    (k_wsum's sum w a^2, finish_body) and the noise scale the next fused command perturbs with, against the oracle
+    (which tests/test_reference_direct.py pins to the reference's _update_distribution)."""
+    task = "navigation" if env == "point_env" else "reach"
+    cfg = S.make_cfg(env, task, None, K, T)
+    cfg.mppi.update_cov = True
+    o = make_backend(O.Oracle, cfg, noise_mode=A.NOISE_PHILOX, seed=3)
+    n = make_backend(native.NativePlanner, cfg, noise_mode=A.NOISE_PHILOX, seed=3)
+    rng = np.random.default_rng(K)
+    nu = n.nu
+    for rep in range(3):
+        ch = (rng.random((K, T)) * 3.0).astype(np.float32)
+        acts = rng.uniform(-2, 2, (K, T, nu)).astype(np.float32)
+        m_o, _ = o.update_only(ch, acts)
+        m_n, _ = n.update_only(ch, acts)
+        assert_close(m_n, m_o, 1e-4, 1e-5, "mean_action")
+        so, sn = o.get_planner_state(), n.get_planner_state()
+        assert_close(np.asarray(sn.cov_action[:nu]), np.asarray(so.cov_action[:nu]), 1e-4, 1e-6, f"cov_action [{rep}]")
+        assert not np.allclose(np.asarray(so.cov_action[:nu]), np.asarray(cfg.mppi.noise_sigma).diagonal())
+    # the adapted scale drives the next fused command (identical planner state on both sides)
+    actors = S.default_actors(env)
+    dof, root = S.initial_dof_state(actors), S.initial_root_state(actors)
+    n.set_planner_state(o.get_planner_state())
+    for b in (o, n):
+        b.set_state(dof, root)
+        b.set_objective(task, np.zeros(2 if env == "point_env" else 7, np.float32), None)
+    a_o, _, _ = o.command()
+    a_n, _, _ = n.command()
+    assert_close(n.read_buffer(A.BUF_ACTIONS), o.read_buffer(A.BUF_ACTIONS), 1e-4, 1e-4, "actions with the adapted scale")
+    assert_close(a_n, a_o, 1e-3, 1e-3, "action")
+    so, sn = o.get_planner_state(), n.get_planner_state()
+    assert_close(np.asarray(sn.cov_action[:nu]), np.asarray(so.cov_action[:nu]), 1e-4, 1e-6, "cov_action after a fused command")
+    o.close()
+    n.close()
+
+
 def test_update_ties_give_nan_like_reference():
     """More than 10 samples tied at the minimum: the multi-modal beta search drives beta to 0 and the reference
     returns NaN weights (m3p2i.py:30-43); the kernel must terminate and agree."""

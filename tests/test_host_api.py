@@ -154,12 +154,28 @@ def test_simple_mode_update_and_progress():
     assert float(torch.linalg.norm(real.robot_pos[0] - goal)) < 0.5 * d0
 
 
+def test_update_cov_through_the_mirror_api():
+    """mppi.update_cov=True through M3P2I.command(): cov_action / scale_tril change from tick to tick and stay positive."""
+    from m3p2i_b200 import scene as S
+    cfg = S.make_cfg("point_env", "navigation", [1.0, 1.0], 64, 12)
+    cfg.mppi.update_cov = True
+    tamp = Tamp(cfg, O.Oracle.for_sim)
+    mp = tamp.motion_planner
+    actors = S.default_actors("point_env")
+    dof, root = torch.from_numpy(S.initial_dof_state(actors)), torch.from_numpy(S.initial_root_state(actors))
+    c0 = mp.cov_action.clone()
+    assert torch.allclose(c0, torch.tensor([3.0, 3.0]))
+    tamp.run_tamp(dof, root, "navigation", torch.tensor([1.0, 1.0]), False)
+    c1 = mp.cov_action.clone()
+    tamp.run_tamp(dof, root, "navigation", torch.tensor([1.0, 1.0]), False)
+    c2 = mp.cov_action.clone()
+    assert not torch.allclose(c0, c1) and not torch.allclose(c1, c2) and (c2 > 0).all()
+    assert torch.allclose(mp.scale_tril, torch.sqrt(c2))
+    tamp.sim.stop_sim()
+
+
 def test_unsupported_options_fail_loudly():
     from m3p2i_b200 import scene as S
-    cfg = S.make_cfg("point_env", "navigation", [1.0, 1.0], 32, 12)
-    cfg.mppi.update_cov = True
-    with pytest.raises(NotImplementedError, match="update_cov"):
-        Tamp(cfg, O.Oracle.for_sim)
     cfg = S.make_cfg("point_env", "navigation", [1.0, 1.0], 32, 12)
     cfg.mppi.sampling_method = "sobol"
     with pytest.raises(ValueError, match="sampling_method"):

@@ -149,3 +149,103 @@ def test_update_matches_reference_on_random_costs(ref, env, mm):
             if env == "panda_env":
                 assert st.beta == pytest.approx(float(planner.beta), rel=1e-12)
     o.close()
+
+
+@pytest.mark.parametrize("env", ["point_env", "panda_env"])
+def test_update_cov_matches_reference(ref, env):
+    """mppi.update_cov=True (mppi.py:508-516): the per-dimension variance update from the weighted second moment of the
+    samples, step 0.7, kappa 0.005, and the noise scale sqrt(cov) the NEXT command perturbs with (mppi.py:394,516):
+    three successive random updates through the reference's _update_distribution against the oracle's update."""
+    G, ref_m3p2i, ref_cost = ref
+    K, T = 128, 12
+    cfg = S.make_cfg(env, "push" if env == "point_env" else "reach", POINT_GOAL if env == "point_env" else None, K, T, device="cpu")
+    cfg.mppi.filter_u = False
+    cfg.mppi.update_cov = True
+    torch.manual_seed(0)
+    planner = ref_m3p2i.M3P2I(cfg, dynamics=lambda s, u, t=None: (s, u), running_cost=lambda s: torch.zeros(K))
+    nu = planner.nu
+    rng = np.random.default_rng(17)
+    o = make_backend(O.Oracle, cfg)
+    actors = S.default_actors(env)
+    o.set_state(S.initial_dof_state(actors), S.initial_root_state(actors))
+    st = o.get_planner_state()
+    assert_close(np.asarray(st.cov_action[:nu]), planner.cov_action.numpy(), 1e-6, 0, "initial cov_action")
+    for rep in range(3):
+        cost_h = (rng.random((K, T)) * 5 + rng.random((K, 1)) * 5).astype(np.float32)
+        actions = rng.uniform(-2.0, 2.0, (K, T, nu)).astype(np.float32)
+        planner._update_distribution(torch.from_numpy(cost_h), torch.from_numpy(actions))
+        mean, info = o.update_only(cost_h, actions)
+        st = o.get_planner_state()
+        assert_close(mean, planner.mean_action.numpy(), 2e-4, 2e-5, f"{env} mean_action [{rep}]")
+        assert_close(np.asarray(st.cov_action[:nu]), planner.cov_action.numpy(), 2e-4, 1e-6, f"{env} cov_action [{rep}]")
+        assert_close(np.sqrt(np.asarray(st.cov_action[:nu])), planner.scale_tril.numpy(), 2e-4, 1e-6, f"{env} scale_tril [{rep}]")
+    # the adapted scale is what the next perturbation uses (mppi.py:394): sampled action = clamp(shifted mean + delta * sqrt(cov))
+    delta = rng.standard_normal((K, T, nu)).astype(np.float32) * 0.1
+    o.set_noise_table(delta)
+    o.set_objective("push" if env == "point_env" else "reach", np.asarray(POINT_GOAL if env == "point_env" else [0.0] * 7, np.float32), None)
+    mean = planner.mean_action.numpy()
+    o.command()
+    act = o.read_buffer(A.BUF_ACTIONS)
+    shifted = np.concatenate([mean[1:], mean[-1:]])
+    lo, hi = np.asarray(cfg.mppi.u_min, np.float32), np.asarray(cfg.mppi.u_max, np.float32)
+    expect = np.clip(shifted[None] + delta * planner.scale_tril.numpy()[None, None], lo, hi)
+    assert_close(act[: K - 1], expect[: K - 1], 2e-4, 2e-5, f"{env} perturbation with the adapted scale")   # row K-1: null action
+    o.close()
+
+
+def _linear_world(K, nx_used=4):
+    """A tiny differentiable world for the callback paths: state [K,4] = (x, vx, y, vy), u = (ax, ay) (only the first
+    two action dimensions act), cost = distance to (1, -1) + 0.1 |u|^2."""
+    def dynamics(state, u, t=None):
+        s = state.clone()
+        s[:, 1] = 0.9 * s[:, 1] + 0.05 * u[:, 0]
+        s[:, 3] = 0.9 * s[:, 3] + 0.05 * u[:, 1]
+        s[:, 0] = s[:, 0] + 0.05 * s[:, 1]
+        s[:, 2] = s[:, 2] + 0.05 * s[:, 3]
+        dynamics.last_u = u
+        return s, u
+
+    def running_cost(state):
+        return torch.sqrt((state[:, 0] - 1.0) ** 2 + (state[:, 2] + 1.0) ** 2) + 0.1 * (dynamics.last_u[:, :2] ** 2).sum(1)
+    return dynamics, running_cost
+
+
+@pytest.mark.parametrize("abs_cost", [False, True])
+def test_simple_mode_matches_reference(ref, monkeypatch, abs_cost):
+    """mppi_mode='simple' (mppi.py:220-233,335-363): classic MPPI with fresh Gaussian noise, lambda * U Sigma^-1 eps
+    control cost, softmin of the total cost at temperature lambda, U += sum_k w_k eps_k. The host mirror (rollouts
+    through the callbacks, softmin + weighted sum through m3p2i_update_only -- here on the oracle backend) against the
+    imported reference planner fed the same noise, five successive commands."""
+    G, ref_m3p2i, ref_cost = ref
+    from m3p2i_aip.planners.motion_planner import mppi as our_mppi
+    from m3p2i_b200 import native
+    monkeypatch.setattr(native, "NativePlanner", O.Oracle)   # the CPU tier has no GPU: the update runs on the oracle
+    K, T = 96, 12
+    cfg = S.make_cfg("point_env", "navigation", [1.0, -1.0], K, T, device="cpu")
+    cfg.mppi.mppi_mode = "simple"
+    cfg.mppi.filter_u = False
+    cfg.mppi.noise_abs_cost = abs_cost
+    cfg.mppi.lambda_ = 0.7
+    cfg.mppi.u_per_command = T
+    cfg.mppi.noise_sigma = [[2.0, 0.3], [0.3, 1.0]]
+    dyn_r, cost_r = _linear_world(K)
+    dyn_o, cost_o = _linear_world(K)
+    torch.manual_seed(1)
+    theirs = ref_m3p2i.M3P2I(cfg, dynamics=dyn_r, running_cost=cost_r)
+    ours = our_mppi.MPPI(cfg, dynamics=dyn_o, running_cost=cost_o)
+    assert not ours.fused
+    U0 = torch.randn(T, 2) * 0.3
+    theirs.U, ours.U = U0.clone(), U0.clone()
+    rng = np.random.default_rng(5)
+    state = torch.tensor([0.0, 0.0, 0.0, 0.0])
+    for tick in range(5):
+        noise = torch.from_numpy((rng.standard_normal((K, T, 2)) @ np.linalg.cholesky(np.array(cfg.mppi.noise_sigma)).T).astype(np.float32))
+        theirs.noise_dist = type("Fixed", (), {"sample": staticmethod(lambda shape, n=noise: n.clone())})()
+        ours._sample_noise = lambda *shape, n=noise: n.clone()
+        a_t = theirs.command(state)
+        a_o = ours.command(state)
+        assert_close(a_o.numpy(), a_t.numpy(), 3e-4, 3e-5, f"simple mode action [{tick}]")
+        assert_close(ours.U.numpy(), theirs.U.numpy(), 3e-4, 3e-5, f"simple mode U [{tick}]")
+        assert_close(ours.weights.numpy(), theirs.weights.numpy(), 3e-3, 1e-7, f"simple mode weights [{tick}]")
+        assert_close(ours.cost_total.numpy(), theirs.cost_total.numpy(), 2e-4, 2e-4, f"simple mode cost_total [{tick}]")
+        state = torch.tensor([0.02 * (tick + 1), 0.1, -0.01 * (tick + 1), -0.1])
