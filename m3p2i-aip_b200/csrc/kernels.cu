@@ -172,12 +172,17 @@ void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, co
     // MINB = 1: the whole grid is one CTA per SM, so the kernel may use the full register file (no spills)
     const bool one_wave = tgrid <= team_sms();
     // dynamic shared memory: the contact accumulators of panda_team.cuh, 7 * CPL float4 per thread
-    const size_t smem = (size_t)7 * (16 / c.lanes) * sizeof(float4) * tb;
+    // + (reach) the deferred cost ingredients, 2 float4 per step and sample
+    const size_t smem = (size_t)7 * (16 / c.lanes) * sizeof(float4) * tb +
+                        (need_refs ? (size_t)(tb / c.lanes) * 2 * c.T * sizeof(float4) : 0);
     static bool attr_set = false;
     if (!attr_set) {
-      const int max_smem = 7 * 2 * (int)sizeof(float4) * kTeamBlockMax;   // CPL = 2, largest CTA: above the 48 KB default
+      // CPL = 2, largest CTA, longest horizon: above the 48 KB default
+      const int max_smem = 7 * 2 * (int)sizeof(float4) * kTeamBlockMax + (kTeamBlockMax / 8) * 2 * kMaxT * (int)sizeof(float4);
       cudaFuncSetAttribute(k_rollout_team<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
       cudaFuncSetAttribute(k_rollout_team<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      cudaFuncSetAttribute(k_rollout_team<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      cudaFuncSetAttribute(k_rollout_team<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
       attr_set = true;
     }
     if (c.lanes == 16 && one_wave) k_rollout_team<1, 1><<<tgrid, tb, smem, st>>>(c, *qp, b);
@@ -257,12 +262,7 @@ __global__ void __launch_bounds__(kStatsBlock) k_stats(const UpdateCfg u, const 
   // multi-modal: the three weight sets (all / first half / second half) are independent searches: one CTA each
   const int s = blockIdx.x;
   int iters = 0;
-  if (u.multi_modal) {
-    for (int i = threadIdx.x; i < Kg; i += kStatsBlock) b.weights[(size_t)s * Kg + i] = 0.0f;
-  } else {
-    for (int i = threadIdx.x; i < 3 * Kg; i += kStatsBlock) b.weights[i] = 0.0f;
-  }
-  __syncthreads();
+  // (the weight rows are zero outside the ranges written below: cleared once at allocation, the ranges never change)
   {
     const int lo = s == 2 ? half : 0, n = s == 0 ? Kg : (s == 1 ? half : Kg - half);
     float v = INFINITY;

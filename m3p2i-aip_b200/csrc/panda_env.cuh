@@ -692,6 +692,41 @@ DEV float panda_cost_from_hand(const Hand& H, float q7, float q8, const Cube& cu
   }
 }
 
+// The reach cost (cost_functions.py:91-114,138-156) split at the point where rows of OTHER samples enter it.
+// reach_parts(): everything a sample knows by itself after a step -- ee position, the three dot products of the hand's
+// z axis with the own cube's axes (the one picked by `sel_axis` of another row is chosen later; first mode: slot 0
+// holds the finished cost_z), and the y-axis alignment term. reach_combine(): the cost once the batch rows are known.
+// Same arithmetic, same order as panda_cost_from_hand's reach branch.
+struct ReachParts {
+  V3 ee, dz;
+  float min_y;
+};
+DEV ReachParts reach_parts(const Hand& H, float q7, float q8, const Cube& cubeA, const RolloutCfg& c, int kg) {
+  const bool second = c.multi_modal && kg >= c.Kg / 2;
+  const V3 lf = H.p + mul(H.R, mk(0.0f, q7, kFingerZ)), rf = H.p + mul(H.R, mk(0.0f, -q8, kFingerZ));
+  ReachParts r;
+  r.ee = mk((lf.x + rf.x) / 2.0f, (lf.y + rf.y) / 2.0f, (lf.z + rf.z) / 2.0f);
+  const M33 C = ref_rotmat(cubeA.qx, cubeA.qy, cubeA.qz, cubeA.qw);
+  if (!second) r.dz = mk(min_axis_cost(H.R.cz, C), 0.0f, 0.0f);
+  else r.dz = mk(dot(H.R.cz, C.cx), dot(H.R.cz, C.cy), dot(H.R.cz, C.cz));
+  r.min_y = min_axis_cost(H.R.cy, C);
+  return r;
+}
+DEV float reach_combine(const ReachParts& r, const RolloutCfg& c, int kg, const PandaRef& ref) {
+  const bool second = c.multi_modal && kg >= c.Kg / 2;
+  V3 g = mk(ref.cube0[0], ref.cube0[1], ref.cube0[2]);
+  if (!second) g.z += c.pre_height_diff;
+  else {
+    g.x -= c.pre_height_diff * c.tilt_cos;
+    g.z += c.pre_height_diff * sqrtf(1.0f - c.tilt_cos * c.tilt_cos);
+  }
+  const V3 d = mk(r.ee.x - g.x, r.ee.y - g.y, r.ee.z - g.z);
+  const float reach = sqrtf(dot(d, d));
+  const float cost_z = !second ? r.dz.x : fabsf(c.tilt_cos - comp(r.dz, ref.sel_axis));
+  const float tilt = cost_z + r.min_y;
+  return 10.0f * reach + 3.0f * tilt;
+}
+
 DEV float panda_cost(const PandaEnv& e, const PandaParams& P, const RolloutCfg& c, int kg, const PandaRef& ref) {
   Hand H;
   H.p = mk(0, 0, 0); H.R.cx = mk(1, 0, 0); H.R.cy = mk(0, 1, 0); H.R.cz = mk(0, 0, 1); H.v = mk(0, 0, 0); H.w = mk(0, 0, 0);

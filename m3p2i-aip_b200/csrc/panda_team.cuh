@@ -417,6 +417,9 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
   unsigned prev_st = 0u, prev_lk = 0u, prev_cc = 0u;   // bit per slot: in contact in the previous sub-step
   M3_DYNAMIC_SMEM(float4, slam_base);
   float4* const slam = slam_base + threadIdx.x;
+  // reach with batch rows from the producer: per sample [T][2] float4 of cost ingredients behind the accumulators
+  const bool defer_reach = use_refs && !producer && c.task == M3P2I_TASK_REACH;
+  float4* const sreach = slam_base + 7 * CPL * blockDim.x + (threadIdx.x / TM) * 2 * T;
 #pragma unroll
   for (int q = 0; q < 7 * CPL; ++q) slam[q * blockDim.x] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 
@@ -519,7 +522,13 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       // ---- cost of the step that just ended (same joint positions as this FK; the drives only changed velocities)
       const int ps = step - 1;
       if (producer) {
-        if (t.tl == 0 && (which == 0 || (which == 1 && c.multi_modal))) ref_publish(b, which, ps, c.epoch, e.cu, !c.multi_modal);
+        // rows 0 / Kg/2 of the batch for every sample's reach cost: plain stores per step, ONE fence + flag at the end
+        // (the consumers finish their costs after their own loop, see defer_reach)
+        if (t.tl == 0 && (which == 0 || (which == 1 && c.multi_modal))) {
+          PandaRef* r = b.refs + ps;
+          if (which == 0) { r->cube0[0] = e.cu.p.x; r->cube0[1] = e.cu.p.y; r->cube0[2] = e.cu.p.z; }
+          if (which == 1 || !c.multi_modal) r->sel_axis = sel_axis_of(e.cu);
+        }
       } else {
         const int src = t.team_base;  // a lane of group 0 holds cubeA
         Cube a;
@@ -527,16 +536,27 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
         a.qx = __shfl_sync(kFull, e.cu.qx, src); a.qy = __shfl_sync(kFull, e.cu.qy, src);
         a.qz = __shfl_sync(kFull, e.cu.qz, src); a.qw = __shfl_sync(kFull, e.cu.qw, src);
         a.v = mk(0, 0, 0); a.w = mk(0, 0, 0);
-        PandaRef ref;
-        if (use_refs) ref = ref_wait(b, ps, c.epoch, c.multi_modal != 0);
-        else { ref.cube0[0] = a.p.x; ref.cube0[1] = a.p.y; ref.cube0[2] = a.p.z; ref.sel_axis = sel_axis_of(a); }
-        const float fx = e.f_table.x + 4.0f * e.f_shelf.x + e.f_cubeb.x, fy = e.f_table.y + 4.0f * e.f_shelf.y + e.f_cubeb.y;
-        const float motion = (fabsf(fx) + fabsf(fy)) > 0.1f ? 1000.0f : 0.0f;
-        const float cost = panda_cost_from_hand(H, e.q[7], e.q[8], a, motion, c, kg, ref);
-        run += cost;
-        J += gam * cost;
-        gam *= c.gamma;
-        if (writer) b.cost_h[(size_t)ps * K + k] = cost;
+        if (defer_reach) {
+          // reach: the cost needs rows of OTHER samples (the producer's refs[ps]); keep what this sample knows now and
+          // finish all T costs after the loop, when the producer is long done -- no hand-over per step
+          const ReachParts rp = reach_parts(H, e.q[7], e.q[8], a, c, kg);
+          if (t.tl == 0) {
+            float4* slot = sreach + 2 * ps;
+            slot[0] = make_float4(rp.ee.x, rp.ee.y, rp.ee.z, rp.min_y);
+            slot[1] = make_float4(rp.dz.x, rp.dz.y, rp.dz.z, 0.0f);
+          }
+        } else {
+          PandaRef ref;
+          if (use_refs) ref = ref_wait(b, ps, c.epoch, c.multi_modal != 0);
+          else { ref.cube0[0] = a.p.x; ref.cube0[1] = a.p.y; ref.cube0[2] = a.p.z; ref.sel_axis = sel_axis_of(a); }
+          const float fx = e.f_table.x + 4.0f * e.f_shelf.x + e.f_cubeb.x, fy = e.f_table.y + 4.0f * e.f_shelf.y + e.f_cubeb.y;
+          const float motion = (fabsf(fx) + fabsf(fy)) > 0.1f ? 1000.0f : 0.0f;
+          const float cost = panda_cost_from_hand(H, e.q[7], e.q[8], a, motion, c, kg, ref);
+          run += cost;
+          J += gam * cost;
+          gam *= c.gamma;
+          if (writer) b.cost_h[(size_t)ps * K + k] = cost;
+        }
       }
     }
     if (last) break;
@@ -849,7 +869,32 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       e.f_cubeb = inv_dt * icb;
     }
   }
-  if (producer) return;
+  if (producer) {
+    if (t.tl == 0 && (which == 0 || (which == 1 && c.multi_modal))) {
+      __threadfence();
+      *(volatile unsigned*)(b.ref_flags + which) = c.epoch + (unsigned)T;
+    }
+    return;
+  }
+  if (defer_reach && t.tl == 0) {
+    // the T reach costs, now that the rows of the batch they read are published: ONE wait for the producer's last
+    // step (flags count steps), then refs[0..T) are plain loads
+    (void)ref_wait(b, T - 1, c.epoch, c.multi_modal != 0);
+#pragma unroll 4
+    for (int ps = 0; ps < T; ++ps) {
+      PandaRef ref;
+      ref.cube0[0] = __ldcg(&b.refs[ps].cube0[0]); ref.cube0[1] = __ldcg(&b.refs[ps].cube0[1]);
+      ref.cube0[2] = __ldcg(&b.refs[ps].cube0[2]); ref.sel_axis = __ldcg(&b.refs[ps].sel_axis);
+      const float4 p0 = sreach[2 * ps], p1 = sreach[2 * ps + 1];
+      ReachParts rp;
+      rp.ee = mk(p0.x, p0.y, p0.z); rp.min_y = p0.w; rp.dz = mk(p1.x, p1.y, p1.z);
+      const float cost = reach_combine(rp, c, kg, ref);
+      run += cost;
+      J += gam * cost;
+      gam *= c.gamma;
+      if (writer) b.cost_h[(size_t)ps * K + k] = cost;
+    }
+  }
   if (writer) { b.cost_sum[k] = run; publish_J(b, c, k, J); }
   if (c.store_env) {
     // arm joints back from their owner lanes (warp-uniform branch: every team of the launch stores or none does)
