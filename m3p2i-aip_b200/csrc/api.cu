@@ -219,11 +219,11 @@ int materialize(H* h) {
 // lanes per sample of the rollout kernel: the lane-cooperative team kernels shorten the per-sample serial chain and
 // win while the GPU is not full; beyond that the redundant work of a team costs more than it hides.
 // cfg.lanes_per_sample: 0 = choose, 1 = thread per sample, 8 / 16 = team of that size.
-// Measured on B200 (profiles/r01_ksweep_lanes_v3.csv), 148 SMs, CTAs of 7 warps:
-//   K <= 14 * SMs (2072): 16 lanes, one CTA per SM, full register file (no spills)     0.31 - 0.35 ms
-//   K <= 28 * SMs (4144):  8 lanes, one CTA per SM, full register file                 0.36 - 0.39 ms
-//   K <= 56 * SMs (8288):  8 lanes, two CTAs per SM (128 registers)                    0.51 - 0.61 ms
-//   larger K: one thread per sample (flat 0.99 ms up to K = 16384, then throughput-bound)
+// Measured on B200 (profiles/r02_ksweep_*.csv), 148 SMs, CTAs of 7 warps, one CTA per SM (full register file):
+//   K <= 14 * SMs (2072): 16 lanes, one wave
+//   K <= 28 * SMs (4144):  8 lanes, one wave
+//   K <= 56 * SMs (8288):  8 lanes, two waves
+//   larger K: one thread per sample (flat up to K = 16384, then throughput-bound)
 int rollout_lanes(const H* h) {
   if (h->cfg.env_type != M3P2I_ENV_PANDA) return 1;
   static int forced = -1;

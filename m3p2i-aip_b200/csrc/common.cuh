@@ -27,6 +27,9 @@ constexpr int kMaxT = M3P2I_MAX_HORIZON;
 // number of floats of one environment in the persistent env buffer (field-major, [field][K])
 constexpr int kPointEnvFloats = 22;
 constexpr int kPandaEnvFloats = 53;
+// panda_env: at most this many link / cube contacts per cube and sub-step are solved (detection order: finger 1,
+// finger 2, hand; link corners in the cube before cube corners in the link); the oracle has the same limit
+constexpr int kLinkCap = 32;
 
 // planner sequences kept on the device, each [T*nu]
 enum Seq { SEQ_MEAN = 0, SEQ_MEAN1, SEQ_MEAN2, SEQ_BEST, SEQ_BEST1, SEQ_BEST2, SEQ_COUNT };

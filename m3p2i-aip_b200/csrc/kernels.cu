@@ -105,8 +105,10 @@ namespace m3 {
 
 // Lane-cooperative variant for panda_env: 16 / CPL lanes per sample (panda_team.cuh), 2 * CPL samples per warp.
 // CTA 0 is the producer of the batch rows read by the reach cost when b.refs is set.
-template <int CPL, int MINB>
-__global__ void __launch_bounds__(kTeamBlockMax, MINB)
+// One CTA per SM (the contact records and accumulators take most of the shared memory): the kernel may use the whole
+// register file (no spills); larger grids run in waves.
+template <int CPL>
+__global__ void __launch_bounds__(kTeamBlockMax, 1)
 k_rollout_team(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
   team_kernel_body<CPL>(c, P, b);
 }
@@ -124,11 +126,10 @@ static int rollout_block(int K) {
   return K <= 148 * 16 * 4 ? 16 : kRolloutBlock;
 }
 
-// CTA size of the team kernel. Each warp carries two samples and the kernel holds 16 warps per SM (128 registers).
-// The rollout is one wave of equally long CTAs, so its duration is set by the SM that received the most warps:
-// pick the warps-per-CTA w in 2..7 that minimises ceil(#CTAs / #SMs) * w, preferring large CTAs (their warps are
-// re-aligned every sub-step and share instruction-cache lines). K = 4096: w = 7 -> 2 CTAs = 14 warps on every SM
-// (w = 8 or 4 would put 16 on most SMs: +15 % time, measured).
+// CTA size of the team kernel (one CTA per SM, up to 7 warps). The rollout runs in waves of equally long CTAs, so its
+// duration is set by the SM that received the most warps: pick the warps-per-CTA w in 2..7 that minimises
+// ceil(#CTAs / #SMs) * w, preferring large CTAs (their warps are re-aligned every sub-step and share
+// instruction-cache lines). K = 4096 with 8-lane teams: w = 7 -> 147 CTAs, one per SM.
 static int team_sms() {
   static int sms = 0;
   if (!sms) {
@@ -169,26 +170,23 @@ void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, co
     const int tb = team_block(c.K, extra, per_warp);
     const int teams_per_block = tb / c.lanes;
     const int tgrid = (c.K + teams_per_block - 1) / teams_per_block + extra;
-    // MINB = 1: the whole grid is one CTA per SM, so the kernel may use the full register file (no spills)
-    const bool one_wave = tgrid <= team_sms();
     // dynamic shared memory: the contact accumulators of panda_team.cuh, 7 * CPL float4 per thread
     // + (reach) the deferred cost ingredients, 2 float4 per step and sample
+    // + the link / cube contact records of a sub-step, one list of kRecStride float4 per (sample, cube)
     const size_t smem = (size_t)7 * (16 / c.lanes) * sizeof(float4) * tb +
+                        (size_t)(tb / c.lanes) * 2 * kRecStride * sizeof(float4) +
                         (need_refs ? (size_t)(tb / c.lanes) * 2 * c.T * sizeof(float4) : 0);
     static bool attr_set = false;
     if (!attr_set) {
       // CPL = 2, largest CTA, longest horizon: above the 48 KB default
-      const int max_smem = 7 * 2 * (int)sizeof(float4) * kTeamBlockMax + (kTeamBlockMax / 8) * 2 * kMaxT * (int)sizeof(float4);
-      cudaFuncSetAttribute(k_rollout_team<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-      cudaFuncSetAttribute(k_rollout_team<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-      cudaFuncSetAttribute(k_rollout_team<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-      cudaFuncSetAttribute(k_rollout_team<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      const int max_smem = 7 * 2 * (int)sizeof(float4) * kTeamBlockMax +
+                           (kTeamBlockMax / 8) * 2 * (kRecStride + kMaxT) * (int)sizeof(float4);
+      cudaFuncSetAttribute(k_rollout_team<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      cudaFuncSetAttribute(k_rollout_team<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
       attr_set = true;
     }
-    if (c.lanes == 16 && one_wave) k_rollout_team<1, 1><<<tgrid, tb, smem, st>>>(c, *qp, b);
-    else if (c.lanes == 16) k_rollout_team<1, 2><<<tgrid, tb, smem, st>>>(c, *qp, b);
-    else if (one_wave) k_rollout_team<2, 1><<<tgrid, tb, smem, st>>>(c, *qp, b);
-    else k_rollout_team<2, 2><<<tgrid, tb, smem, st>>>(c, *qp, b);
+    if (c.lanes == 16) k_rollout_team<1><<<tgrid, tb, smem, st>>>(c, *qp, b);
+    else k_rollout_team<2><<<tgrid, tb, smem, st>>>(c, *qp, b);
   } else {
     k_rollout<M3P2I_ENV_PANDA><<<grid, block, 0, st>>>(c, *qp, b);
   }

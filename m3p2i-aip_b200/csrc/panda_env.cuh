@@ -394,15 +394,17 @@ DEV bool boxes_near(const OBox3& a, const OBox3& b, float margin) {
 // Corners of box `ba` (body A) against box `bb` (body B), each hit solved as the pair (A, B) with the normal out of bb
 // -- or, FLIP, as the pair (B, A) with the normal reversed (the corners of the second body of a pair in the first).
 // `lam` = the 8 accumulator slots of this corner set (nullptr: plain solves), `prev` / `cur` = bit per corner: in
-// contact in the previous / this sub-step. Returns the impulse received by the FIRST body of the solved pair.
+// contact in the previous / this sub-step; `room` = contacts this corner set may still take (counted down).
+// Returns the impulse received by the FIRST body of the solved pair.
 template <bool FLIP>
 DEV V3 corners_vs_box3(Dyn3& A, const OBox3& ba, Dyn3& B, const OBox3& bb, float mu, float h, const PandaParams& P,
-                       float4* lam, unsigned prev, unsigned& cur, bool first) {
+                       float4* lam, unsigned prev, unsigned& cur, bool first, int& room) {
   V3 got = mk(0, 0, 0);
   for (int i = 0; i < 8; ++i) {
     const V3 p = box_corner(ba, i);
     V3 n; float depth;
     if (!point_in_box(p, bb, P.contact_margin, n, depth)) continue;
+    if (room-- <= 0) continue;   // the list of this cube is full (kLinkCap): the contact is ignored
     cur |= 1u << i;
     if (lam) {
       const bool warm = (prev >> i) & 1u;
@@ -540,14 +542,15 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
     for (int p = 0; p < passes; ++p) {
       for (int sw = 0; sw < P.link_sweeps && lnear; ++sw) {
         const bool first = p == 0 && sw == 0;
+        int room[2] = {kLinkCap, kLinkCap};   // link contacts per cube (the same ones in every sweep: positions are fixed)
         for (int f = 0; f < 3; ++f)
           for (int i = 0; i < 2; ++i) {
             if (asleep[i] || !((lnear >> (2 * f + i)) & 1u)) continue;
             const float mu = 0.5f * (P.robot_mu + P.cube_mu[i]);
             const int s0 = 32 + 32 * f + 16 * i;
             unsigned c0 = 0u, c1 = 0u;
-            V3 got = corners_vs_box3<false>(L[f], lbox[f], C[i], cbox[i], mu, h, P, lam + s0, (prev[s0 >> 5] >> (s0 & 31)) & 0xffu, c0, first);
-            got = got + corners_vs_box3<true>(C[i], cbox[i], L[f], lbox[f], mu, h, P, lam + s0 + 8, (prev[s0 >> 5] >> ((s0 & 31) + 8)) & 0xffu, c1, first);
+            V3 got = corners_vs_box3<false>(L[f], lbox[f], C[i], cbox[i], mu, h, P, lam + s0, (prev[s0 >> 5] >> (s0 & 31)) & 0xffu, c0, first, room[i]);
+            got = got + corners_vs_box3<true>(C[i], cbox[i], L[f], lbox[f], mu, h, P, lam + s0 + 8, (prev[s0 >> 5] >> ((s0 & 31) + 8)) & 0xffu, c1, first, room[i]);
             cur[s0 >> 5] |= (c0 | (c1 << 8)) << (s0 & 31);
             if (i == 1) imp_cubeb = imp_cubeb - got;   // `got` = impulse on the link; cubeB received the opposite
           }
@@ -555,8 +558,9 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
       if (cc_near) {
         const float mu = 0.5f * (P.cube_mu[0] + P.cube_mu[1]);
         unsigned c0 = 0u, c1 = 0u;
-        V3 got = corners_vs_box3<false>(C[0], cbox[0], C[1], cbox[1], mu, h, P, lam + 16, (prev[0] >> 16) & 0xffu, c0, p == 0);
-        got = got + corners_vs_box3<true>(C[1], cbox[1], C[0], cbox[0], mu, h, P, lam + 24, (prev[0] >> 24) & 0xffu, c1, p == 0);
+        int room = 16;
+        V3 got = corners_vs_box3<false>(C[0], cbox[0], C[1], cbox[1], mu, h, P, lam + 16, (prev[0] >> 16) & 0xffu, c0, p == 0, room);
+        got = got + corners_vs_box3<true>(C[1], cbox[1], C[0], cbox[0], mu, h, P, lam + 24, (prev[0] >> 24) & 0xffu, c1, p == 0, room);
         cur[0] |= (c0 << 16) | (c1 << 24);
         imp_cubeb = imp_cubeb - got;                   // `got` = impulse on cubeA
       }
@@ -570,8 +574,9 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
           S.v = mk(0, 0, 0); S.w = mk(0, 0, 0); S.x = sb.c; S.im = 0.0f; S.ii = 0.0f; S.axis = mk(0, 0, 0); S.slide = 0.0f; S.ims = 0.0f;
           const bool acc = k == first_box[i];
           unsigned c0 = 0u;
+          int room = 8;
           const V3 got = corners_vs_box3<false>(C[i], cbox[i], S, sb, 0.5f * (P.cube_mu[i] + P.st[k].mu), h, P,
-                                                acc ? lam + 8 * i : nullptr, (prev[0] >> (8 * i)) & 0xffu, c0, p == 0);
+                                                acc ? lam + 8 * i : nullptr, (prev[0] >> (8 * i)) & 0xffu, c0, p == 0, room);
           if (acc) cur[0] |= c0 << (8 * i);
           if (k == P.idx_table && P.report_cube) imp_table = imp_table - got;
           if (k == P.idx_shelf && P.report_cube) imp_shelf = imp_shelf - got;

@@ -281,59 +281,70 @@ DEV LinkHit link_hit(bool hit, V3 n, float depth, V3 pt, V3 hv, V3 hw, V3 hp, V3
   return s;
 }
 
-// Serial application of the link contacts found by lanes [src0, src0+G) (hb = warp ballot of s.hit); returns the sum
-// of the impulses on the link. The equations of solve_contact3_acc for a kinematic link (one sliding DoF for a finger)
-// against a free cube; `L` = this lane's accumulator of the slot (prepared by warm_prepare when `first`).
-template <int G>
-DEV V3 apply_link_hits(const LinkHit& s, unsigned hb, int src0, bool mine, V3 axis, float& slide, float ims, V3& v, V3& w,
-                       float im, float ii, float mu, float4& L, bool first) {
-  const int lane = threadIdx.x & 31;
+// The link / cube contacts of a sub-step are detected ONCE (positions do not move inside a sub-step) and kept as
+// RECORDS in shared memory, one list per (sample, cube) in the solve order (link 0, 1, 2; corners of the link in the
+// cube, then corners of the cube in the link; ascending corner). A record is four float4:
+//   [0] n, target   [1] rc, an   [2] vl0, ikn   [3] rc x n, index of the slot's accumulator in the CTA's accumulators
+// At most kLinkCap records per cube (further contacts, in detection order, are ignored -- oracle and thread-per-sample
+// kernel do the same). kRecStride = float4 per list; the odd 4-word pad puts the lists of a warp in different banks.
+constexpr int kRecStride = 4 * kLinkCap + 1;
+
+// One visit of the serial Gauss-Seidel chain: the equations of solve_contact3_acc for a kinematic link (one sliding DoF
+// for a finger) against a free cube, geometry terms from the record, accumulator of the slot read and written in
+// shared memory (one lane per cube walks the chain). `first`: the
+// slot's first visit of the sub-step applies its warm start (prepared by warm_prepare at detection). The link of the
+// record (bits 24.. of its last word) selects the sliding DoF: slide[0] / slide[1] for the fingers, none for the hand.
+// Returns the impulse on the link when WANT_SUM (cubeB's contacts are reported), else zero.
+template <bool WANT_SUM>
+DEV V3 solve_link_record(const float4* r, float4* lam_base, V3 ycol, float* slide, float ims_f, V3& v, V3& w, float im,
+                         float ii, float mu, bool first) {
+  const float4 q0 = r[0], q1 = r[1], q2 = r[2], q3 = r[3];
+  const V3 n = mk(q0.x, q0.y, q0.z), rc = mk(q1.x, q1.y, q1.z), vl0 = mk(q2.x, q2.y, q2.z), rcn = mk(q3.x, q3.y, q3.z);
+  const float target = q0.w, an = q1.w, ikn = q2.w;
+  const int meta = __float_as_int(q3.w), f = meta >> 24;
+  // link f: finger 1 slides along +y of the hand, finger 2 along -y, the hand box (f = 2) has no sliding DoF
+  const V3 axis = f == 0 ? ycol : (f == 1 ? -ycol : mk(0, 0, 0));
+  const float ims = f < 2 ? ims_f : 0.0f;
+  float sl = f == 1 ? slide[1] : slide[0];
+  float4* const Lp = lam_base + (meta & 0xffffff);
+  const float4 Lj = *Lp;
   V3 acc = mk(0, 0, 0);
-  unsigned todo = fold<G>(hb);
-  while (todo) {
-    const int j = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const int src = src0 + j;
-    const V3 n = shfl3(s.n, src), rcn = shfl3(s.rcn, src), rc = shfl3(s.rc, src), vl0 = shfl3(s.vl0, src);
-    const float an = __shfl_sync(kFull, s.an, src), ikn = __shfl_sync(kFull, s.ikn, src);
-    const float target = __shfl_sync(kFull, s.target, src);
-    const float4 Lj = shfl4(L, src);
-    if (!(mine && ((hb >> src) & 1u))) continue;
-    if (first) {
-      const V3 Pw = Lj.x * n + mk(Lj.y, Lj.z, Lj.w);   // on the link; the cube receives -Pw
-      slide += ims * dot(axis, Pw);
-      v = v - im * Pw;
-      w = w - ii * cross(rc, Pw);
-      acc = acc + Pw;
-    }
-    const float vn0 = dot(vl0, n) + slide * an - (dot(v, n) + dot(w, rcn));
-    const float ln = fmaxf(Lj.x + (target - vn0) * ikn, 0.0f);
-    const float dj = ln - Lj.x;
-    slide += ims * an * dj;
-    v = v - (dj * im) * n;
-    w = w - (dj * ii) * rcn;
-    const V3 rv = (vl0 + slide * axis) - (v + cross(w, rc));
-    const float vn = dot(rv, n);
-    V3 t = rv - vn * n;
-    const float vt2 = dot(t, t);
-    V3 lt = mk(Lj.y, Lj.z, Lj.w);
-    if (vt2 >= 1e-18f) {
-      const float ivt = rsqrtf(vt2), vt = vt2 * ivt;
-      t = ivt * t;
-      const V3 rct = cross(rc, t);
-      const float at = dot(axis, t);
-      const float kt = ims * at * at + im + ii * dot(rct, rct);
-      lt = lt - __fdividef(vt, kt) * t;
-    }
-    const float lim = mu * ln, m2 = dot(lt, lt);
-    if (m2 > lim * lim) lt = (lim * rsqrtf(m2)) * lt;
-    const V3 Pt = lt - mk(Lj.y, Lj.z, Lj.w);
-    slide += ims * dot(axis, Pt);
-    v = v - im * Pt;
-    w = w - ii * cross(rc, Pt);
-    acc = acc + dj * n + Pt;
-    if (lane == src) L = make_float4(ln, lt.x, lt.y, lt.z);
+  if (first) {
+    const V3 Pw = Lj.x * n + mk(Lj.y, Lj.z, Lj.w);   // on the link; the cube receives -Pw
+    sl += ims * dot(axis, Pw);
+    v = v - im * Pw;
+    w = w - ii * cross(rc, Pw);
+    if (WANT_SUM) acc = Pw;
   }
+  const float vn0 = dot(vl0, n) + sl * an - (dot(v, n) + dot(w, rcn));
+  const float ln = fmaxf(Lj.x + (target - vn0) * ikn, 0.0f);
+  const float dj = ln - Lj.x;
+  sl += ims * an * dj;
+  v = v - (dj * im) * n;
+  w = w - (dj * ii) * rcn;
+  const V3 rv = (vl0 + sl * axis) - (v + cross(w, rc));
+  const float vn = dot(rv, n);
+  V3 t = rv - vn * n;
+  const float vt2 = dot(t, t);
+  V3 lt = mk(Lj.y, Lj.z, Lj.w);
+  if (vt2 >= 1e-18f) {
+    const float ivt = rsqrtf(vt2), vt = vt2 * ivt;
+    t = ivt * t;
+    const V3 rct = cross(rc, t);
+    const float at = dot(axis, t);
+    const float kt = ims * at * at + im + ii * dot(rct, rct);
+    lt = lt - __fdividef(vt, kt) * t;
+  }
+  const float lim = mu * ln, m2 = dot(lt, lt);
+  if (m2 > lim * lim) lt = (lim * rsqrtf(m2)) * lt;
+  const V3 Pt = lt - mk(Lj.y, Lj.z, Lj.w);
+  sl += ims * dot(axis, Pt);
+  v = v - im * Pt;
+  w = w - ii * cross(rc, Pt);
+  *Lp = make_float4(ln, lt.x, lt.y, lt.z);
+  if (f == 0) slide[0] = sl;
+  if (f == 1) slide[1] = sl;
+  if (WANT_SUM) acc = acc + dj * n + Pt;
   return acc;
 }
 
@@ -419,7 +430,9 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
   float4* const slam = slam_base + threadIdx.x;
   // reach with batch rows from the producer: per sample [T][2] float4 of cost ingredients behind the accumulators
   const bool defer_reach = use_refs && !producer && c.task == M3P2I_TASK_REACH;
-  float4* const sreach = slam_base + 7 * CPL * blockDim.x + (threadIdx.x / TM) * 2 * T;
+  // link / cube contact records of the current sub-step: the list of the own cube (kRecStride float4 per list)
+  float4* const srec = slam_base + 7 * CPL * blockDim.x + ((threadIdx.x / TM) * 2 + g) * kRecStride;
+  float4* const sreach = slam_base + 7 * CPL * blockDim.x + (blockDim.x / TM) * 2 * kRecStride + (threadIdx.x / TM) * 2 * T;
 #pragma unroll
   for (int q = 0; q < 7 * CPL; ++q) slam[q * blockDim.x] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 
@@ -669,65 +682,102 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       lam_st[sl] = warm_prepare(lam_st[sl], sh0[sl].hit && ((prev_st >> sl) & 1u), sh0[sl].n, 0.5f * (mu_c + P.st[k0].mu), P.warm_start);
       if (sh0[sl].hit) cur_st |= 1u << sl;
     }
-    unsigned live = 0xffffffu;  // link contact slots (pair fi, direction/slot phs) not yet known to be empty
+    // ---- link / cube contacts of this sub-step: detection ONCE, by all corner lanes, into the record list of the own
+    // cube (shared memory). Both groups detect at the same time (group g: link f against cube g); the serial order
+    // only matters for the solves below.
+    int nrec = 0;                  // records in the list of the own cube
+    unsigned nmax[2] = {0u, 0u};   // warp-uniform: longest list of cubeA / cubeB in the warp
+    const bool any_link = __any_sync(kFull, lnear != 0u);
+    if (any_link) {
+      __syncwarp();   // the accumulators below were last written by the group's solves of the previous sub-step
+      int cnt = 0;
+#pragma unroll 1
+      for (int f = 0; f < 3; ++f) {
+        const bool mine = (lnear >> f) & 1u;
+        if (__any_sync(kFull, mine)) {
+          OBox3 lb;
+          lb.c = f == 0 ? lc[0] : (f == 1 ? lc[1] : lc[2]); lb.R = H.R; lb.half = f < 2 ? fhalf : hhalf;
+          const V3 axis = f == 0 ? H.R.cy : (f == 1 ? -H.R.cy : mk(0, 0, 0));
+          const float ims = f < 2 ? 1.0f / P.finger_mass : 0.0f;
+          const float mu = 0.5f * (P.robot_mu + mu_c);
+#pragma unroll 1
+          for (int phs = 0; phs < 2 * CPL; ++phs) {
+            // ph 0: corners of the link box in the cube, normal out of the cube;
+            // ph 1: corners of the cube in the link box, normal out of the link -> solve with -n
+            const int ph = phs / CPL, sl = phs - ph * CPL;
+            const V3 pt = ph == 0 ? box_corner(lb, t.c + sl * G) : x + ((CPL > 1 && sl > 0) ? ra[CPL - 1] : ra[0]);
+            OBox3 bx;
+            bx.c = sel3(ph == 0, cb.c, lb.c); bx.half = sel3(ph == 0, cb.half, lb.half);
+            bx.R.cx = sel3(ph == 0, cb.R.cx, lb.R.cx); bx.R.cy = sel3(ph == 0, cb.R.cy, lb.R.cy);
+            bx.R.cz = sel3(ph == 0, cb.R.cz, lb.R.cz);
+            V3 n = mk(0, 0, 0);
+            float depth = 0.0f;
+            const bool hit = mine && point_in_box(pt, bx, P.contact_margin, n, depth);
+            const unsigned hb = __ballot_sync(kFull, hit);
+            if (!hb) continue;
+            const unsigned gb = (hb >> t.group_base) & ((1u << G) - 1u);   // hits of the own group, bit = lane in group
+            const int pos = cnt + __popc(gb & ((1u << t.c) - 1u));
+            cnt += __popc(gb);
+            if (hit && pos < kLinkCap) {
+              const float sg = ph == 0 ? 1.0f : -1.0f;
+              const LinkHit lh = link_hit(hit, sg * n, depth, pt, H.v, H.w, H.p, axis, ims, x, im, ii, inv_h, P);
+              // accumulator of this lane's slot (f, direction, corner slot) of the own cube: warm start from the
+              // previous sub-step of this step, applied by the slot's first visit below
+              const int slot = f * (2 * CPL) + phs;
+              float4* Ls = slam + slot * blockDim.x;
+              *Ls = warm_prepare(*Ls, (prev_lk >> slot) & 1u, lh.n, mu, P.warm_start);
+              cur_lk |= 1u << slot;
+              float4* r = srec + 4 * pos;
+              r[0] = make_float4(lh.n.x, lh.n.y, lh.n.z, lh.target);
+              r[1] = make_float4(lh.rc.x, lh.rc.y, lh.rc.z, lh.an);
+              r[2] = make_float4(lh.vl0.x, lh.vl0.y, lh.vl0.z, lh.ikn);
+              r[3] = make_float4(lh.rcn.x, lh.rcn.y, lh.rcn.z, __int_as_float((f << 24) | (slot * (int)blockDim.x + (int)threadIdx.x)));
+            }
+          }
+          cnt = min(cnt, kLinkCap);
+        }
+      }
+      // longest list of cubeA / cubeB in the warp: the bounds of the (warp-uniform) loops of the sweeps
+      nrec = cnt;
+      nmax[0] = __reduce_max_sync(kFull, g == 0 ? (unsigned)cnt : 0u);
+      nmax[1] = __reduce_max_sync(kFull, g == 1 ? (unsigned)cnt : 0u);
+      __syncwarp();   // records and prepared accumulators are read by the other lanes of the group
+    }
 
 #pragma unroll 1
     for (int p = 0; p < c.passes; ++p) {
-      // (a) links against the cubes in the order (f, cubeA), (f, cubeB); pair (f, i) is worked by group i.
-      // P.link_sweeps sweeps: the finger - cube - finger chain of a grasp only settles after a few sweeps over its
-      // own contacts. `live` remembers which (pair, direction, slot) found no contact at all in this sub-step
-      // (positions are fixed), so later sweeps and passes skip their detection.
-      if (__any_sync(kFull, lnear != 0u)) {
+      // (a) links against the cubes. The serial order of the model is (f, cubeA), (f, cubeB) for f = 0, 1, 2 in every
+      // sweep; cubeA's whole list followed by cubeB's gives the same result (contacts of different cubes only meet in
+      // a finger's sliding speed, and those of the same finger keep their order). The first lane of the cube's group
+      // walks the list (it alone reads and writes the accumulators of the records); the cube's new velocity and the
+      // fingers' sliding speeds go back to the replicas afterwards. P.link_sweeps sweeps: the finger - cube - finger
+      // chain of a grasp only settles after a few sweeps over its own contacts.
+      if (nmax[0] | nmax[1]) {
+        const float ims_f = 1.0f / P.finger_mass, mu = 0.5f * (P.robot_mu + mu_c);
 #pragma unroll 1
         for (int sw = 0; sw < P.link_sweeps; ++sw) {
           const bool first = p == 0 && sw == 0;
+          if (nmax[0]) {
+            const int lead = t.team_base;
+            const bool mine = t.lane == lead;
 #pragma unroll 1
-          for (int fi = 0; fi < 6; ++fi) {
-            const int f = fi >> 1, i = fi & 1;
-            const bool mine = g == i && ((lnear >> f) & 1u);
-            if (!((live >> (4 * fi)) & 0xfu) || !__any_sync(kFull, mine)) continue;
-            OBox3 lb;
-            lb.c = f == 0 ? lc[0] : (f == 1 ? lc[1] : lc[2]); lb.R = H.R; lb.half = f < 2 ? fhalf : hhalf;
-            const V3 axis = f == 0 ? H.R.cy : (f == 1 ? -H.R.cy : mk(0, 0, 0));
-            const float ims = f < 2 ? 1.0f / P.finger_mass : 0.0f;
-            float sl_f = f == 0 ? slide[0] : (f == 1 ? slide[1] : 0.0f);
-            const float mu = 0.5f * (P.robot_mu + mu_c);
+            for (int j = 0; j < (int)nmax[0]; ++j)
+              if (mine && j < nrec) (void)solve_link_record<false>(srec + 4 * j, slam_base, H.R.cy, slide, ims_f, v, w, im, ii, mu, first);
+            const V3 vl = shfl3(v, lead), wl = shfl3(w, lead);
+            if (g == 0) { v = vl; w = wl; }
+            slide[0] = __shfl_sync(kFull, slide[0], lead); slide[1] = __shfl_sync(kFull, slide[1], lead);
+          }
+          if (nmax[1]) {
+            const int lead = t.team_base + G;
+            const bool mine = t.lane == lead;
             V3 got = mk(0, 0, 0);
 #pragma unroll 1
-            for (int phs = 0; phs < 2 * CPL; ++phs) {
-              // ph 0: corners of the link box in the cube, normal out of the cube;
-              // ph 1: corners of the cube in the link box, normal out of the link -> solve with -n
-              if (!((live >> (4 * fi + phs)) & 1u)) continue;
-              const int ph = phs / CPL, sl = phs - ph * CPL;
-              const V3 pt = ph == 0 ? box_corner(lb, t.c + sl * G) : x + ((CPL > 1 && sl > 0) ? ra[CPL - 1] : ra[0]);
-              OBox3 bx;
-              bx.c = sel3(ph == 0, cb.c, lb.c); bx.half = sel3(ph == 0, cb.half, lb.half);
-              bx.R.cx = sel3(ph == 0, cb.R.cx, lb.R.cx); bx.R.cy = sel3(ph == 0, cb.R.cy, lb.R.cy);
-              bx.R.cz = sel3(ph == 0, cb.R.cz, lb.R.cz);
-              V3 n = mk(0, 0, 0);
-              float depth = 0.0f;
-              const bool hit = mine && point_in_box(pt, bx, P.contact_margin, n, depth);
-              const unsigned hb = __ballot_sync(kFull, hit);
-              if (!hb) { live &= ~(1u << (4 * fi + phs)); continue; }
-              const float sg = ph == 0 ? 1.0f : -1.0f;
-              const LinkHit lh = link_hit(hit, sg * n, depth, pt, H.v, H.w, H.p, axis, ims, x, im, ii, inv_h, P);
-              // accumulator of this lane's slot (f, direction, corner slot) of the own cube, in shared memory
-              const int slot = f * (2 * CPL) + phs;
-              float4* Ls = slam + slot * blockDim.x;
-              float4 Lv = *Ls;
-              if (first) {
-                Lv = warm_prepare(Lv, hit && ((prev_lk >> slot) & 1u), lh.n, mu, P.warm_start);
-                if (hit) cur_lk |= 1u << slot;
-              }
-              got = got + apply_link_hits<G>(lh, hb, t.team_base + G * i, mine, axis, sl_f, ims, v, w, im, ii, mu, Lv, first);
-              if (hit) *Ls = Lv;
-            }
-            if (mine && i == 1) imp_cubeb = imp_cubeb - got;
-            // the finger's sliding speed is shared by both groups: take it from the group that worked the pair
-            const float sl = __shfl_sync(kFull, sl_f, t.team_base + G * i);
-            const bool worked = __shfl_sync(kFull, (int)mine, t.team_base + G * i) != 0;
-            if (worked && f == 0) slide[0] = sl;
-            if (worked && f == 1) slide[1] = sl;
+            for (int j = 0; j < (int)nmax[1]; ++j)
+              if (mine && j < nrec) got = got + solve_link_record<true>(srec + 4 * j, slam_base, H.R.cy, slide, ims_f, v, w, im, ii, mu, first);
+            const V3 vl = shfl3(v, lead), wl = shfl3(w, lead);
+            got = shfl3(got, lead);
+            if (g == 1) { v = vl; w = wl; imp_cubeb = imp_cubeb - got; }
+            slide[0] = __shfl_sync(kFull, slide[0], lead); slide[1] = __shfl_sync(kFull, slide[1], lead);
           }
         }
       }

@@ -356,6 +356,10 @@ static inline void o_panda_init(OPandaEnv* e, const M3P2IPandaScene* sc, const f
   }
 }
 
+/* At most this many link / cube contacts per cube and sub-step are solved (detection order: finger 1, finger 2, hand;
+ * link corners in the cube before cube corners in the link). The kernels keep the list in shared memory (kLinkCap). */
+#define O_LINK_CAP 32
+
 /* One detected contact of a sub-step. Positions are fixed inside a sub-step, so detection runs once; the passes
  * then visit the records in the fixed solve order. */
 typedef struct {
@@ -430,13 +434,15 @@ static inline void o_solve_one(const OContact* c, float h, const M3P2IPandaScene
 
 /* corners of box `ba` (body A) against `bb` (body B) -> contact records (normal from B to A; flip: the records are for
  * the pair (B, A) with the normal reversed, as o_corners_vs_box3). `slots` = the 8 accumulators of this corner set or
- * NULL; `sub` = 1-based sub-step index inside the current step(). Returns the new count. */
+ * NULL; `sub` = 1-based sub-step index inside the current step(); `room` = records the list may still take (further
+ * contacts are ignored). Returns the new count. */
 static inline int o_detect(OContact* out, int cnt, OSolv3* A, const OBox3* ba, OSolv3* B, const OBox3* bb, float mu,
-                           const M3P2IPandaScene* sc, int flip, OLam* slots, int sub) {
+                           const M3P2IPandaScene* sc, int flip, OLam* slots, int sub, int room) {
   for (int i = 0; i < 8; ++i) {
     float p[3], n[3], depth;
     o_box_corner(ba, i, p);
     if (!o_point_in_box(p, bb, sc->contact_margin, n, &depth)) continue;
+    if (room-- <= 0) continue;   /* the list of this cube is full: the contact is ignored */
     OContact* c = &out[cnt++];
     if (!flip) { c->A = A; c->B = B; memcpy(c->n, n, 12); }
     else { c->A = B; c->B = A; c->n[0] = -n[0]; c->n[1] = -n[1]; c->n[2] = -n[2]; }
@@ -562,23 +568,27 @@ static inline void o_panda_step(OPandaEnv* e, const M3P2IPandaScene* sc, const M
      * contacts of a cube with its FIRST near fixed box (its support); further fixed boxes use the plain solve. */
     OContact lk[3 * 2 * 16], ccl[16], st[2 * M3P2I_MAX_STATIC * 8];
     int n_lk = 0, n_cc = 0, n_st = 0;
+    int lk_left[2] = {O_LINK_CAP, O_LINK_CAP};   /* at most O_LINK_CAP link contacts per cube, in detection order */
     for (int f = 0; f < 3; ++f)
       for (int i = 0; i < 2; ++i) {
         if (asleep[i] || !lnear[f][i]) continue;
         float mu = 0.5f * (sc->robot_mu + bp[i]->mu);
-        n_lk = o_detect(lk, n_lk, &L[f], &lbox[f], &C[i], &cbox[i], mu, sc, 0, cache.lk[f][i][0], s + 1);
-        n_lk = o_detect(lk, n_lk, &C[i], &cbox[i], &L[f], &lbox[f], mu, sc, 1, cache.lk[f][i][1], s + 1);
+        int n0 = n_lk;
+        n_lk = o_detect(lk, n_lk, &L[f], &lbox[f], &C[i], &cbox[i], mu, sc, 0, cache.lk[f][i][0], s + 1, lk_left[i]);
+        lk_left[i] -= n_lk - n0; n0 = n_lk;
+        n_lk = o_detect(lk, n_lk, &C[i], &cbox[i], &L[f], &lbox[f], mu, sc, 1, cache.lk[f][i][1], s + 1, lk_left[i]);
+        lk_left[i] -= n_lk - n0;
       }
     if (cc_near) {
       float mu = 0.5f * (bp[0]->mu + bp[1]->mu);
-      n_cc = o_detect(ccl, n_cc, &C[0], &cbox[0], &C[1], &cbox[1], mu, sc, 0, cache.cc[0], s + 1);
-      n_cc = o_detect(ccl, n_cc, &C[1], &cbox[1], &C[0], &cbox[0], mu, sc, 1, cache.cc[1], s + 1);
+      n_cc = o_detect(ccl, n_cc, &C[0], &cbox[0], &C[1], &cbox[1], mu, sc, 0, cache.cc[0], s + 1, 16);
+      n_cc = o_detect(ccl, n_cc, &C[1], &cbox[1], &C[0], &cbox[0], mu, sc, 1, cache.cc[1], s + 1, 16);
     }
     for (int i = 0; i < 2; ++i)
       for (int k = 0; k < sc->n_static; ++k) {
         if (asleep[i] || !o_boxes_near(&cbox[i], &sbox[k], sc->contact_margin)) continue;
         n_st = o_detect(st, n_st, &C[i], &cbox[i], &S[k], &sbox[k], 0.5f * (bp[i]->mu + sc->statics[k].mu), sc, 0,
-                        k == first_box[i] ? cache.st[i] : NULL, s + 1);
+                        k == first_box[i] ? cache.st[i] : NULL, s + 1, 8);
       }
     const int sweeps = sc->link_sweeps > 0 ? sc->link_sweeps : 2;
     for (int p = 0; p < cfg->solver_passes; ++p) {

@@ -88,6 +88,13 @@ inline unsigned ballot(bool p, int site) {
   finish();
   return m;
 }
+inline unsigned reduce_max(unsigned v, int site) {
+  publish(v, site);
+  unsigned m = 0u;
+  for (int i = 0; i < 32; ++i) m = std::max(m, (unsigned)fetch(i));
+  finish();
+  return m;
+}
 }  // namespace emu
 
 #define threadIdx (emu::me().tid)
@@ -97,6 +104,8 @@ inline unsigned ballot(bool p, int site) {
 #define __shfl_xor_sync(mask, v, x) emu::shfl((v), (int)(emu::W->cur ^ (x)), __LINE__)
 #define __ballot_sync(mask, p) emu::ballot((p), __LINE__)
 #define __any_sync(mask, p) (emu::ballot((p), __LINE__) != 0u)
+#define __syncwarp() ((void)emu::ballot(true, __LINE__))
+#define __reduce_max_sync(mask, v) emu::reduce_max((v), __LINE__)
 #define __syncthreads() do { fprintf(stderr, "emu: __syncthreads is not emulated (run with align = 0)\n"); abort(); } while (0)
 #define M3_PIN_VALUES9(a, b, c, d, e, f, g, h, i) do { } while (0)
 #define M3_DYNAMIC_SMEM(type, name) type* name = static_cast<type*>(emu::W->smem)
@@ -105,6 +114,8 @@ static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline int __float_as_int(float a) { int r; memcpy(&r, &a, 4); return r; }
+static inline float __int_as_float(int a) { float r; memcpy(&r, &a, 4); return r; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 template <typename T> static inline T __ldcg(const T* p) { return *p; }

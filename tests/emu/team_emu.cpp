@@ -116,7 +116,7 @@ int emu_team_rollout_actions(const M3P2IConfig* cfg, const M3P2IPandaScene* scen
   g_launch = {&c, &P, &b, cpl};
   emu::Warp* w = new emu::Warp();
   for (int l = 0; l < 32; ++l) w->lane[l].stack = static_cast<char*>(malloc(kStack));
-  std::vector<float4> smem((size_t)7 * cpl * block_threads + (size_t)(block_threads / lanes) * 2 * T);
+  std::vector<float4> smem((size_t)7 * cpl * block_threads + (size_t)(block_threads / lanes) * 2 * (kRecStride + T));
   long coll = 0;
   for (int blk = 0; blk < grid; ++blk)   // CTA 0 (the producer of the reach rows) first, as on the GPU
     for (int wi = 0; wi < block_threads / 32; ++wi) coll += run_warp(*w, blk, block_threads, wi, smem.data());

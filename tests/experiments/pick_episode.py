@@ -1,6 +1,6 @@
 """Closed-loop reactive pick on the native backend: reach -> pick (-> place), task switching by the thresholds of
 PLANNER_AIF_PANDA (task_planner.py:57-75). Prints the trace; exit code 0 if the cube ends within 5 cm of the goal.
-usage: [PICK_BACKEND=oracle] [PICK_SAMPLING=halton|philox|philox-spline] python tests/experiments/pick_episode.py [K] [H] [ticks]"""
+usage: [PICK_BACKEND=oracle] [PICK_REAL=oracle|native] [PICK_SAMPLING=halton|philox|philox-spline] python tests/experiments/pick_episode.py [K] [H] [ticks]"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,11 +14,13 @@ K = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 TICKS = int(sys.argv[3]) if len(sys.argv) > 3 else 900
 factory = None
-if os.environ.get("PICK_BACKEND") == "oracle":
+if os.environ.get("PICK_BACKEND") == "oracle" or os.environ.get("PICK_REAL") == "oracle":
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
     O.set_threads(os.cpu_count())
-    factory = O.Oracle.for_sim
+    factory = O.Oracle.for_sim if os.environ.get("PICK_BACKEND") == "oracle" else None
+# PICK_REAL=oracle|native: backend of the K=1 "real world" env only (default: the planner's)
+real_factory = {"oracle": lambda: O.Oracle.for_sim, "native": lambda: None}.get(os.environ.get("PICK_REAL"), lambda: factory)()
 
 
 class Tamp:
@@ -38,7 +40,7 @@ class Tamp:
 cfg = S.make_cfg("panda_env", "reach", None, K, H)
 cfg.mppi.sampling_method = os.environ.get("PICK_SAMPLING", "philox" if factory is None else "halton")
 tamp = Tamp(cfg)
-real = wrapper.IsaacGymWrapper(cfg.isaacgym, "panda_env", num_envs=1, device="cpu", backend_factory=factory)
+real = wrapper.IsaacGymWrapper(cfg.isaacgym, "panda_env", num_envs=1, device="cpu", backend_factory=real_factory)
 for _ in range(30):
     real.step()
 task, goal = "reach", torch.zeros(7)

@@ -196,7 +196,7 @@ def _reactive_pick(factory, K, sampling, ticks=450):
     """reach -> pick -> place with the switching thresholds of PLANNER_AIF_PANDA (task_planner.py:57-75,96): reach until
     the gripper is pre_height_diff + 0.005 above cubeA, pick towards cubeB + (0, 0, 0.055), place once the cubes are
     aligned within 3 cm in the plane. Returns (final task, closest approach of cubeA to the pre-place pose, ticks)."""
-    cfg = S.make_cfg("panda_env", "reach", None, K, 16)
+    cfg = S.make_cfg("panda_env", "reach", None, K, 12)   # horizon of the reference's mppi/panda.yaml
     cfg.mppi.sampling_method = sampling
     planner = Planner(cfg, factory)
     real = wrapper.IsaacGymWrapper(cfg.isaacgym, "panda_env", num_envs=1, device="cpu", backend_factory=factory)
