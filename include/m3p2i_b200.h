@@ -16,6 +16,7 @@
  *   m3p2i_set_objective            <- Objective.update_objective (cost_functions.py:15-17) and
  *                                     M3P2I.update_gripper_command (m3p2i.py:10-14)
  *   m3p2i_set_noise_table          <- the `delta` attribute of MPPI (mppi.py:100,386-392)
+ *   m3p2i_set_noise_halton_spline  <- MPPI.get_samples (mppi.py:458-478) built on the device
  *   m3p2i_command                  <- MPPI.command (mppi.py:211-264): shift, sample, T-step rollout
  *                                     (mppi.py:275-332 -> reactive_tamp.py:63-73 -> isaacgym_wrapper.py:
  *                                     354-360 + cost_functions.py:19-36), softmin weights
@@ -272,6 +273,17 @@ int m3p2i_set_noise_table(m3p2i_handle h, const float* delta);
 /* Noise row [T,nu] of GLOBAL sample 0, for shards that do not own it (table mode, single-mode panda reach: every
  * sample's cost reads sample 0's cube position, cost_functions.py:98). NULL drops it. */
 int m3p2i_set_noise_row0(m3p2i_handle h, const float* row0);
+/* Builds the reference's once-sampled halton-spline table ON THE DEVICE for this shard's global samples (replaces
+ * MPPI.get_samples, mppi.py:458-478, the K * nu scipy calls of skill_utils.bspline, skill_utils.py:9-22, and
+ * generate_gaussian_halton_samples, mppi_utils.py:80-104): n_knots = T / knot_scale points per (sample, dimension) of
+ * the Halton sequence in n_knots * nu dimensions -> sqrt(2) erfinv(2 u - 1) -> FITPACK smoothing spline (degree,
+ * smoothing = 0.5 in the reference) sampled at T points. perms = NULL gives the plain Halton sequence (the reference's
+ * use_ghalton=False branch, mppi_utils.py:82-87); perms = uint16 [n_knots * nu][perm_stride], row d a permutation of
+ * 0 .. prime(d)-1, gives the generalised (digit-scrambled) sequence of ghalton.GeneralizedHalton(perms)
+ * (mppi_utils.py:88-95: pass ghalton.EA_PERMS[:ndims], padded to perm_stride). Also fills the row of global sample 0
+ * when this shard does not own it (m3p2i_set_noise_row0). Needs noise_mode = M3P2I_NOISE_TABLE. */
+int m3p2i_set_noise_halton_spline(m3p2i_handle h, int knot_scale, int degree, float smoothing, const uint16_t* perms,
+                                  int perm_stride);
 /* Writes the noise the kernel uses (table or Philox) as [K_local, T, nu]; before delta[-1]=0 is applied. */
 int m3p2i_get_noise(m3p2i_handle h, float* out_delta);
 

@@ -711,6 +711,62 @@ int m3p2i_set_noise_table(m3p2i_handle h, const float* delta) {
   return 0;
 }
 
+int m3p2i_set_noise_halton_spline(m3p2i_handle h, int knot_scale, int degree, float smoothing, const uint16_t* perms,
+                                  int perm_stride) {
+  if (!h) return fail(M3P2I_ERR_ARG, "null handle");
+  const int K = h->cfg.num_samples, T = h->cfg.horizon, nu = h->cfg.nu;
+  if (knot_scale < 1 || degree < 1 || degree > 3) return fail(M3P2I_ERR_ARG, "knot_scale >= 1 and degree 1..3 expected");
+  const int m = T / knot_scale, ndims = m * nu;
+  if (m <= degree) return fail(M3P2I_ERR_ARG, "horizon / knot_scale must exceed the spline degree (the reference YAMLs: horizon >= 12)");
+  if (m > 16) return fail(M3P2I_ERR_ARG, "at most 16 knot points per spline (horizon / knot_scale)");
+  if (!(smoothing > 0.0f)) return fail(M3P2I_ERR_ARG, "smoothing factor must be positive");
+  std::vector<int> bases(ndims);
+  {
+    int found = 0;
+    for (int c = 2; found < ndims; ++c) {
+      bool prime = true;
+      for (int j = 2; j * j <= c; ++j) if (c % j == 0) { prime = false; break; }
+      if (prime) bases[found++] = c;
+    }
+  }
+  if (perms) {
+    if (perm_stride < bases[ndims - 1]) return fail(M3P2I_ERR_ARG, "perm_stride is smaller than the largest base");
+    for (int d = 0; d < ndims; ++d) {   // every row must be a permutation of its base's digits
+      std::vector<char> seen(bases[d], 0);
+      for (int q = 0; q < bases[d]; ++q) {
+        const int v = perms[(size_t)d * perm_stride + q];
+        if (v >= bases[d] || seen[v]) return fail(M3P2I_ERR_ARG, "perms rows must be permutations of 0 .. base-1");
+        seen[v] = 1;
+      }
+    }
+  }
+  CK(cudaSetDevice(h->device));
+  DevBuf<int> dbases;
+  DevBuf<unsigned short> dperms;
+  CK(dbases.alloc(ndims));
+  CK(cudaMemcpyAsync(dbases.p, bases.data(), sizeof(int) * ndims, cudaMemcpyHostToDevice, h->stream));
+  if (perms) {
+    CK(dperms.alloc((size_t)ndims * perm_stride));
+    CK(cudaMemcpyAsync(dperms.p, perms, sizeof(unsigned short) * (size_t)ndims * perm_stride, cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(h->noise.alloc((size_t)K * T * nu));
+  launch_halton_spline(h->noise.p, K, h->cfg.sample_offset, T, nu, m, degree, (double)smoothing, dbases.p,
+                       perms ? dperms.p : nullptr, perm_stride, h->stream);
+  CK(cudaGetLastError());
+  h->have_noise = true;
+  if (h->cfg.sample_offset != 0) {
+    CK(h->noise_row0.alloc((size_t)T * nu));
+    launch_halton_spline(h->noise_row0.p, 1, 0, T, nu, m, degree, (double)smoothing, dbases.p, perms ? dperms.p : nullptr,
+                         perm_stride, h->stream);
+    CK(cudaGetLastError());
+    h->have_row0 = true;
+  }
+  const cudaError_t e = cudaStreamSynchronize(h->stream);
+  dbases.release(); dperms.release();
+  CK(e);
+  return 0;
+}
+
 int m3p2i_set_noise_row0(m3p2i_handle h, const float* row0) {
   if (!h) return fail(M3P2I_ERR_ARG, "null handle");
   if (!row0) { h->have_row0 = false; return 0; }

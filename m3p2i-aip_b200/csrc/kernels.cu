@@ -100,6 +100,7 @@ k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename
 }  // namespace m3
 
 #include "panda_team.cuh"
+#include "halton_spline.cuh"
 
 namespace m3 {
 
@@ -665,6 +666,12 @@ __global__ void k_transpose(const float* in, float* out, int rows, int cols) {
   x = blockIdx.y * 32 + threadIdx.x; y = blockIdx.x * 32 + threadIdx.y;
   for (int j = 0; j < 32; j += 8)
     if (x < rows && y + j < cols) out[(size_t)(y + j) * rows + x] = tile[threadIdx.x][threadIdx.y + j];
+}
+
+void launch_halton_spline(float* out, int K, int offset, int T, int nu, int m, int degree, double smoothing,
+                          const int* bases, const unsigned short* perms, int perm_stride, cudaStream_t st) {
+  const int n = K * nu, block = 64;   // a few KB of fp64 scratch per thread: small CTAs spread it over all SMs
+  k_halton_spline<<<(n + block - 1) / block, block, 0, st>>>(out, K, offset, T, nu, m, degree, smoothing, bases, perms, perm_stride);
 }
 
 void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st) {

@@ -63,6 +63,9 @@ void launch_sim_cost(int env_type, const RolloutCfg& c, const PointParams* pp, c
                      float* out_cost, cudaStream_t st);
 void launch_sim_links(const PandaParams* qp, const float* env, float* links /*[K][39]*/, int K, cudaStream_t st);
 void launch_noise_dump(const RolloutCfg& c, float* out /*[T][nu][K]*/, cudaStream_t st);
+// halton-spline noise table (halton_spline.cuh): out [T][nu][K] for global samples offset .. offset + K
+void launch_halton_spline(float* out, int K, int offset, int T, int nu, int m, int degree, double smoothing,
+                          const int* bases, const unsigned short* perms, int perm_stride, cudaStream_t st);
 // [rows][cols] -> [cols][rows]
 void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st);
 

@@ -99,6 +99,11 @@ class MPPI():
         self.seed_val = int(getattr(m, "seed_val", 0))
         self._delta = None
         self._delta_uploaded = False
+        self._delta_on_device = False
+        self.knot_scale, self.degree = 4, 2           # mppi.py:169,173
+        # digit permutations of the generalised Halton sequence, uint16 [n_knots * nu, stride] (ghalton.EA_PERMS when the
+        # package is installed, mppi_utils.py:88-95); None = the plain sequence (the reference's use_ghalton=False branch)
+        self.halton_perms = getattr(m, "halton_perms", None)
         self._info = None
         self.gripper_command = None
         self.state = None
@@ -148,12 +153,15 @@ class MPPI():
     # ------------------------------------------------------------------ noise table (mppi.py:386-392,458-483)
     @property
     def delta(self):
+        if self._delta is None and self._delta_on_device:
+            return torch.from_numpy(self.backend.get_noise())   # the table lives on the device; read back on demand
         return self._delta
 
     @delta.setter
     def delta(self, value):
         self._delta = value
         self._delta_uploaded = False
+        self._delta_on_device = False
 
     def get_samples(self, sample_shape, **kwargs):
         if self.sampling_method == "halton":
@@ -171,6 +179,13 @@ class MPPI():
 
     def _ensure_noise(self):
         if self.sampling_method in ("philox", "philox-spline") and self._delta is None:
+            return
+        if self.sampling_method == "halton" and self._delta is None:
+            # the once-sampled table of mppi.py:458-478 (Halton knots, erfinv, one smoothing spline per sample and
+            # dimension) is built by the backend for its own shard: on the device, no K * nu scipy calls
+            if not self._delta_on_device:
+                self.backend.set_noise_halton_spline(self.knot_scale, self.degree, 0.5, perms=self.halton_perms)
+                self._delta_on_device = True
             return
         if self.sampling_method == "random" or self._delta is None:
             self.delta = self.get_samples(self.K, base_seed=0)

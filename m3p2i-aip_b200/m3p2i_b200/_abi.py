@@ -114,6 +114,7 @@ PROTOTYPES = {
     "m3p2i_set_objective": (C.c_int, [vp, C.c_int, fp, C.c_int, C.c_int]),
     "m3p2i_set_noise_table": (C.c_int, [vp, fp]),
     "m3p2i_set_noise_row0": (C.c_int, [vp, fp]),
+    "m3p2i_set_noise_halton_spline": (C.c_int, [vp, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_uint16), C.c_int]),
     "m3p2i_get_noise": (C.c_int, [vp, fp]),
     "m3p2i_get_planner_state": (C.c_int, [vp, C.POINTER(PlannerState)]),
     "m3p2i_set_planner_state": (C.c_int, [vp, C.POINTER(PlannerState)]),

@@ -107,6 +107,16 @@ class NativePlanner:
             raise ValueError(f"delta must be [{self.K},{self.T},{self.nu}]")
         self._ck(self.fn["m3p2i_set_noise_table"](self.h, A.as_fp(d)), "m3p2i_set_noise_table")
 
+    def set_noise_halton_spline(self, knot_scale=4, degree=2, smoothing=0.5, perms=None):
+        """The reference's once-sampled halton-spline table (mppi.py:458-478) built on the device for this shard's global
+        samples. perms: None (plain Halton) or uint16 [n_knots * nu, stride] digit permutations (ghalton.EA_PERMS)."""
+        pp, stride = None, 0
+        if perms is not None:
+            perms = np.ascontiguousarray(perms, np.uint16)
+            pp, stride = perms.ctypes.data_as(C.POINTER(C.c_uint16)), int(perms.shape[1])
+        self._ck(self.fn["m3p2i_set_noise_halton_spline"](self.h, int(knot_scale), int(degree), float(smoothing), pp, stride),
+                 "m3p2i_set_noise_halton_spline")
+
     def set_noise_row0(self, row0):
         d = None if row0 is None else _f32(row0)
         self._ck(self.fn["m3p2i_set_noise_row0"](self.h, A.as_fp(d)), "m3p2i_set_noise_row0")

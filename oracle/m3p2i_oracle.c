@@ -15,6 +15,7 @@
 
 #include "point_env.h"
 #include "panda_env.h"
+#include "halton_spline.h"
 
 static int g_threads = 1;
 void orc_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
@@ -191,6 +192,22 @@ int orc_set_noise_row0(Oracle* o, const float* row0) {
   if (!o->delta_row0) o->delta_row0 = (float*)malloc(n * 4);
   memcpy(o->delta_row0, row0, n * 4);
   return 0;
+}
+
+int orc_set_noise_halton_spline(Oracle* o, int knot_scale, int degree, float smoothing, const unsigned short* perms,
+                                int perm_stride) {
+  if (!o || knot_scale < 1) return -1;
+  const int K = o->cfg.num_samples, T = o->cfg.horizon, nu = o->cfg.nu;
+  float* d = (float*)malloc((size_t)K * T * nu * 4);
+  omp_set_num_threads(g_threads);
+  int rc = hs_table(K, o->cfg.sample_offset, T, nu, knot_scale, degree, (double)smoothing, perms, perm_stride, d);
+  if (!rc) rc = orc_set_noise_table(o, d);
+  if (!rc && o->cfg.sample_offset != 0) {
+    rc = hs_table(1, 0, T, nu, knot_scale, degree, (double)smoothing, perms, perm_stride, d);
+    if (!rc) rc = orc_set_noise_row0(o, d);
+  }
+  free(d);
+  return rc;
 }
 
 int orc_get_noise(Oracle* o, float* out) {
@@ -798,5 +815,19 @@ int orc_panda_fk(const M3P2IPandaScene* s, const float* q, const float* qd, floa
   if (!s || !q || !link_state) return -1;
   float zero[9] = {0};
   o_panda_links(s, q, qd ? qd : zero, link_state);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ halton-spline noise table (halton_spline.h) */
+int orc_halton_spline_table(int K, int offset, int T, int nu, int knot_scale, int degree, double smoothing,
+                            const unsigned short* perms, int perm_stride, float* out) {
+  if (!out || K <= 0 || T <= 0 || T > 256 || nu <= 0 || nu > 16 || knot_scale <= 0) return -1;
+  omp_set_num_threads(g_threads);
+  return hs_table(K, offset, T, nu, knot_scale, degree, smoothing, perms, perm_stride, out);
+}
+/* skill_utils.bspline on one knot vector */
+int orc_bspline_samples(const float* cv, int m, int T, int degree, double smoothing, float* out) {
+  if (!cv || !out || m <= degree || m > HS_MAXM || T <= 0 || T > 256) return -1;
+  hs_bspline_samples(cv, m, T, degree, smoothing, out);
   return 0;
 }

@@ -22,7 +22,7 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("m3p2i_oracle.c", "m3p2i_oracle.h", "point_env.h", "panda_env.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("m3p2i_oracle.c", "m3p2i_oracle.h", "point_env.h", "panda_env.h", "halton_spline.h")]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "m3p2i_b200.h"))
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
@@ -40,6 +40,9 @@ def lib():
             "orc_set_threads": (None, [C.c_int]),
             "orc_get_threads": (C.c_int, []),
             "orc_panda_fk": (C.c_int, [C.POINTER(A.PandaScene), fp, fp, fp]),
+            "orc_halton_spline_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                                  C.POINTER(C.c_uint16), C.c_int, fp]),
+            "orc_bspline_samples": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, C.c_double, fp]),
         }
         for name, (res, args) in protos.items():
             fn = getattr(L, name)
@@ -116,6 +119,14 @@ class Oracle:
         if d is not None:
             assert d.shape == (self.K, self.T, self.nu)
         self._ck(self.L.fn["m3p2i_set_noise_table"](self.h, A.as_fp(d)), "set_noise_table")
+
+    def set_noise_halton_spline(self, knot_scale=4, degree=2, smoothing=0.5, perms=None):
+        pp, stride = None, 0
+        if perms is not None:
+            perms = np.ascontiguousarray(perms, np.uint16)
+            pp, stride = perms.ctypes.data_as(C.POINTER(C.c_uint16)), int(perms.shape[1])
+        self._ck(self.L.fn["m3p2i_set_noise_halton_spline"](self.h, int(knot_scale), int(degree), float(smoothing), pp, stride),
+                 "set_noise_halton_spline")
 
     def set_noise_row0(self, row0):
         d = None if row0 is None else _f32(row0)
@@ -252,4 +263,27 @@ def panda_fk(scene, q, qd=None):
     rc = L.orc_panda_fk(C.byref(scene), A.as_fp(qq), A.as_fp(qv), A.as_fp(out))
     if rc:
         raise RuntimeError("orc_panda_fk failed")
+    return out
+
+
+def bspline_samples(cv, T, degree=2, smoothing=0.5):
+    """skill_utils.bspline (scipy splrep s=0.5 + splev) restated in C (halton_spline.h)."""
+    cv = _f32(cv)
+    out = np.empty(T, np.float32)
+    if lib().orc_bspline_samples(A.as_fp(cv), len(cv), int(T), int(degree), float(smoothing), A.as_fp(out)):
+        raise RuntimeError("orc_bspline_samples failed")
+    return out
+
+
+def halton_spline_table(K, T, nu, knot_scale=4, degree=2, smoothing=0.5, offset=0, perms=None):
+    """delta [K, T, nu] of the halton-spline mode (mppi.py:458-478) for global samples offset .. offset + K.
+    perms: None (plain Halton) or uint16 [n_knots * nu, stride] digit permutations (generalised Halton)."""
+    out = np.empty((K, T, nu), np.float32)
+    pp, stride = None, 0
+    if perms is not None:
+        perms = np.ascontiguousarray(perms, np.uint16)
+        pp, stride = perms.ctypes.data_as(C.POINTER(C.c_uint16)), perms.shape[1]
+    if lib().orc_halton_spline_table(int(K), int(offset), int(T), int(nu), int(knot_scale), int(degree), float(smoothing),
+                                     pp, stride, A.as_fp(out)):
+        raise RuntimeError("orc_halton_spline_table failed")
     return out
