@@ -30,6 +30,7 @@
 namespace m3 {
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr float kGripReach = 0.12f;   // hand box centre to the farthest point of a finger box, minus the hand box radius
 
 template <int CPL>
 struct TeamShape {
@@ -436,10 +437,15 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
 #pragma unroll
   for (int q = 0; q < 7 * CPL; ++q) slam[q * blockDim.x] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 
+  // bounding radii of the link boxes; hand + fingers lie inside a sphere of radius hrad + kGripReach about the hand
+  // box centre (the fingers reach 0.12 m from it: finger joint offset + finger box + stroke)
+  const float frad = sqrtf(P.finger_half[0] * P.finger_half[0] + P.finger_half[1] * P.finger_half[1] + P.finger_half[2] * P.finger_half[2]);
+  const float hrad = sqrtf(P.hand_half[0] * P.hand_half[0] + P.hand_half[1] * P.hand_half[1] + P.hand_half[2] * P.hand_half[2]);
+  bool was_asleep = false;   // own cube slept through the previous sub-step of this rollout
+  int k0_keep = 0;           // its support box then
   const int n_iter = T * ns;
 #pragma unroll 1
-  for (int it = 0; it <= n_iter; ++it) {
-    const int step = it / ns, s = it - step * ns;
+  for (int it = 0, step = 0, s = 0; it <= n_iter; ++it, s = (s + 1 == ns ? 0 : s + 1), step += (s == 0)) {
     const bool last = it == n_iter;
     // Re-align the warps of the CTA once per sub-step: they then walk the same stretch of this (large) loop body at
     // about the same time and share its instruction-cache lines instead of evicting each other's.
@@ -460,8 +466,9 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       float ssn[7], scs[7], sqd[7];
 #pragma unroll
       for (int i = 0; i < 7; ++i) { ssn[i] = 0.0f; scs[i] = 1.0f; sqd[i] = 0.0f; }
+      int stepi = step, si = s;   // step / sub-step of iteration it + l
 #pragma unroll 1
-      for (int l = 0; l < TM; ++l) {
+      for (int l = 0; l < TM; ++l, si = (si + 1 == ns ? 0 : si + 1), stepi += (si == 0)) {
         const int iti = it + l;
         if (iti > n_iter) break;
         const bool lasti = iti == n_iter;
@@ -497,8 +504,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
           if (qn > up_o) { qn = up_o; vo = 0.0f; }
           qo = qn;
           // state row of a finished step: (q1, qd1) from lane 0, (q2, qd2) from lane 1 (reactive_tamp.py:66-69)
-          const int stepi = iti / ns;
-          if (valid && t.tl < 2 && iti - stepi * ns == ns - 1)
+          if (valid && t.tl < 2 && si == ns - 1)
             reinterpret_cast<float2*>(b.states + (size_t)stepi * K + k)[t.tl] = make_float2(qo, vo);
         }
       }
@@ -587,8 +593,28 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     }
     const V3 fhalf = mk(P.finger_half[0], P.finger_half[1], P.finger_half[2]);
     const V3 hhalf = mk(P.hand_half[0], P.hand_half[1], P.hand_half[2]);
-    const float frad = sqrtf(dot(fhalf, fhalf)), hrad = sqrtf(dot(hhalf, hhalf));
     float slide[2] = {e.qd[7], e.qd[8]};
+    // ---- dormant cubes: a cube that slept through the previous sub-step (velocity zero, supported, nothing near) and
+    // whose distance to the gripper exceeds the bounding sphere of hand + fingers plus its own radius and the contact
+    // margin sleeps through this one too -- every test of the full path below would come out as before (nothing of the
+    // cube moved, no link box can pass its centre-distance pre-test). When that holds for every cube of the warp, all
+    // the cube work of the sub-step is skipped; only the weight the support carries is booked.
+    bool asleep = true;
+    bool dormant;
+    {
+      const V3 dh = lc[2] - e.cu.p;
+      const float rfar = hrad + kGripReach + rad_own + P.contact_margin;
+      dormant = was_asleep && dot(dh, dh) > rfar * rfar;
+    }
+    if (__all_sync(kFull, dormant)) {
+      const float wgt = P.cube_mass[g] * P.gravity * h;   // the support carries the weight
+      if (k0_keep == P.idx_table && P.report_cube) imp_table.z -= wgt;
+      if (k0_keep == P.idx_shelf && P.report_cube) imp_shelf.z -= wgt;
+      if (g == 1) imp_cubeb.z += wgt;
+#pragma unroll
+      for (int sl = 0; sl < CPL; ++sl) lam_st[sl] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      prev_st = 0u; prev_lk = 0u; prev_cc = 0u;
+    } else {
     OBox3 cb;  // own cube
     cb.c = e.cu.p; cb.R = quat_to_R(e.cu.qx, e.cu.qy, e.cu.qz, e.cu.qw); cb.half = half_own;
     // keep the nine entries as values: under register pressure ptxas otherwise re-derives them from the quaternion
@@ -650,7 +676,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     // ---- 3. sleeping (decided per cube, i.e. per group): an (almost) motionless cube that rests on its first near
     // fixed box with at least three corners and has no link and no other cube within the contact margin is neither
     // moved nor solved in this sub-step
-    bool asleep = false;
+    asleep = false;
     {
       int sup = 0;
 #pragma unroll
@@ -844,6 +870,9 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     }
     prev_st = cur_st; prev_lk = cur_lk; prev_cc = cur_cc;
     e.cu.v = v; e.cu.w = w;
+    k0_keep = k0;
+    }   // not dormant
+    was_asleep = asleep;
 #pragma unroll
     for (int f = 0; f < 2; ++f) {
       slide[f] = clampf(slide[f], -P.qd_limit[7 + f], P.qd_limit[7 + f]);
@@ -857,7 +886,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
         const float mu = 0.5f * (P.robot_mu + P.st[ks].mu);
         // one bounding sphere for hand + fingers first (centre = hand box centre, radius covers the three boxes)
         OBox3 gb;
-        gb.c = lc[2]; gb.R = H.R; gb.half = mk(hrad + 0.12f, 0.0f, 0.0f);
+        gb.c = lc[2]; gb.R = H.R; gb.half = mk(hrad + kGripReach, 0.0f, 0.0f);
         const bool grip_near = boxes_near(gb, sb, 0.0f);
 #pragma unroll 1
         for (int f = 0; f < 3 && grip_near; ++f) {

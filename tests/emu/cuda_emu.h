@@ -104,6 +104,7 @@ inline unsigned reduce_max(unsigned v, int site) {
 #define __shfl_xor_sync(mask, v, x) emu::shfl((v), (int)(emu::W->cur ^ (x)), __LINE__)
 #define __ballot_sync(mask, p) emu::ballot((p), __LINE__)
 #define __any_sync(mask, p) (emu::ballot((p), __LINE__) != 0u)
+#define __all_sync(mask, p) (emu::ballot((p), __LINE__) == 0xffffffffu)
 #define __syncwarp() ((void)emu::ballot(true, __LINE__))
 #define __reduce_max_sync(mask, v) emu::reduce_max((v), __LINE__)
 #define __syncthreads() do { fprintf(stderr, "emu: __syncthreads is not emulated (run with align = 0)\n"); abort(); } while (0)
