@@ -220,10 +220,9 @@ int materialize(H* h) {
 // win while the GPU is not full; beyond that the redundant work of a team costs more than it hides.
 // cfg.lanes_per_sample: 0 = choose, 1 = thread per sample, 8 / 16 = team of that size.
 // Measured on B200 (profiles/r02_ksweep_*.csv), 148 SMs, CTAs of 7 warps, one CTA per SM (full register file):
-//   K <= 14 * SMs (2072): 16 lanes, one wave
-//   K <= 28 * SMs (4144):  8 lanes, one wave
-//   K <= 56 * SMs (8288):  8 lanes, two waves
-//   larger K: one thread per sample (flat up to K = 16384, then throughput-bound)
+//   K <= 14 * SMs (2072):  16 lanes, one wave
+//   K <= 84 * SMs (12432):  8 lanes, one to three waves of 4144 samples (0.13 / 0.25 / 0.37-0.40 ms rollout at rest)
+//   larger K: one thread per sample (0.44 ms flat up to K = 16384, then throughput-bound: 0.54 ms at K = 32768)
 int rollout_lanes(const H* h) {
   if (h->cfg.env_type != M3P2I_ENV_PANDA) return 1;
   static int forced = -1;
@@ -235,7 +234,7 @@ int rollout_lanes(const H* h) {
   if (want == 1 || want == 8 || want == 16) return want;
   const int sms = h->sm_count > 0 ? h->sm_count : 148;
   if (h->cfg.num_samples <= 14 * sms) return 16;
-  if (h->cfg.num_samples <= 56 * sms) return 8;
+  if (h->cfg.num_samples <= 84 * sms) return 8;
   return 1;
 }
 

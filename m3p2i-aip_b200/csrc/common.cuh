@@ -137,6 +137,21 @@ struct RolloutBufs {
 };
 
 // ------------------------------------------------------------------ small math
+// ------------------------------------------------------------------ programmatic dependent launch
+// The three kernels of a command depend on each other grid-to-grid. Launched with programmatic stream serialization the
+// next kernel's CTAs are scheduled as soon as the previous grid has issued launch_dependents and SM resources are free;
+// they then wait in pdl_wait() until the previous grid has completed and its writes are visible. That takes the
+// launch latency of k_stats / k_wsum out of the command (the rollout's last CTAs finish while they are being set up).
+DEV void pdl_wait() {
+#ifndef M3_EMU
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+DEV void pdl_launch_dependents() {
+#ifndef M3_EMU
+  asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
 DEV float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 DEV float signf(float v) { return v < 0.0f ? -1.0f : 1.0f; }
 

@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(kRolloutBlock)
 k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename EnvOf<ENV>::Params P, const RolloutBufs b) {
   using Env = typename EnvOf<ENV>::Env;
   constexpr int NU = EnvOf<ENV>::NU;
+  pdl_launch_dependents();   // k_stats may be set up while this grid runs; it waits for its completion (pdl_wait)
   const bool use_refs = ENV == M3P2I_ENV_PANDA && b.refs != nullptr;
   if (use_refs && blockIdx.x == 0) {
     if (ENV == M3P2I_ENV_PANDA) produce_refs(c, P, b, threadIdx.x);
@@ -111,6 +112,7 @@ namespace m3 {
 template <int CPL>
 __global__ void __launch_bounds__(kTeamBlockMax, 1)
 k_rollout_team(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
+  pdl_launch_dependents();   // k_stats may be set up while this grid runs; it waits for its completion (pdl_wait)
   team_kernel_body<CPL>(c, P, b);
 }
 
@@ -194,6 +196,18 @@ void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, co
   ++*launches;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (host side)
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ------------------------------------------------------------------ block reductions (fixed order => reproducible)
 DEV float warp_sum(float v) {
 #pragma unroll
@@ -253,6 +267,8 @@ __global__ void __launch_bounds__(kStatsBlock) k_stats(const UpdateCfg u, const 
   __shared__ int is_last;
   const int Kg = u.Kg, half = Kg / 2;
   const float* J = b.J_global;
+  pdl_launch_dependents();   // k_wsum may be set up now; it waits for this grid before it reads anything
+  pdl_wait();                // the rollout (or whatever precedes on the stream) has completed
   // sharded over peer memory: J_global is the local mailbox; every rank's slice has landed once its flag is up
   Stats* S = b.stats;
   if (b.peer.n) wait_flags(b.peer.jflag_local, b.peer.n, b.peer.epoch, b.peer.timeout_ms, b.peer.error,
@@ -333,7 +349,7 @@ __global__ void __launch_bounds__(kStatsBlock) k_stats(const UpdateCfg u, const 
 }
 
 void launch_stats(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches) {
-  k_stats<<<u.multi_modal ? 3 : 1, kStatsBlock, 0, st>>>(u, b);
+  launch_pdl(k_stats, dim3(u.multi_modal ? 3 : 1), dim3(kStatsBlock), 0, st, u, b);
   ++*launches;
 }
 
@@ -344,15 +360,22 @@ void launch_stats(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int*
 DEV void finish_body(const UpdateCfg& u, const UpdateBufs& b, float* smean);
 
 __global__ void __launch_bounds__(kSumBlock) k_wsum(const UpdateCfg u, const UpdateBufs b) {
-  extern __shared__ float smean[];  // [T*nu], used by the last CTA when the finish step is fused in
+  extern __shared__ float smean[];  // [T*nu] + [T*T], used by the last CTA when the finish step is fused in
   __shared__ float sh[32];
   __shared__ int is_last;
   const int K = u.K, Kg = u.Kg, half = Kg / 2, TN = u.T * u.nu, j = blockIdx.x;
+  pdl_wait();   // k_stats has completed (weights, best indices)
   if (j == TN) {
     float a = 0.0f;
     for (int k = threadIdx.x; k < K; k += kSumBlock) a += b.cost_sum[k];
     a = block_sum<kSumBlock>(a, sh);
     if (threadIdx.x == 0) b.partials[6 * TN] = a;
+    if (u.fuse_finish && !b.peer.n) {
+      // single rank: this CTA knows the mean already, so cost_total (mppi.py:282-284,325) is written here, in parallel
+      // with the weighted sums, instead of by the last CTA
+      const float mean_cost = a / (float)Kg;
+      for (int k = threadIdx.x; k < K; k += kSumBlock) b.cost_total[k] = b.cost_sum[k] + mean_cost;
+    }
   } else {
   const float* plane = b.actions + (size_t)j * K;
   const float* w0 = b.weights + u.offset;
@@ -423,7 +446,7 @@ __global__ void __launch_bounds__(kSumBlock) k_wsum(const UpdateCfg u, const Upd
 }
 
 void launch_wsum(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches) {
-  k_wsum<<<u.T * u.nu + 1, kSumBlock, sizeof(float) * u.T * u.nu, st>>>(u, b);
+  launch_pdl(k_wsum, dim3(u.T * u.nu + 1), dim3(kSumBlock), sizeof(float) * (u.T * u.nu + u.T * u.T), st, u, b);
   ++*launches;
 }
 
@@ -436,6 +459,10 @@ DEV void finish_body(const UpdateCfg& u, const UpdateBufs& b, float* smean /* sh
   const float a2 = u.step_size_mean, a1 = (float)(1.0 - (double)u.step_size_mean);
   const volatile float* part = b.partials;   // written by other CTAs in the fused launch
   float* seq = b.seq;
+  float* sfilt = smean + TN;                 // the Savitzky-Golay matrix [T][T], staged once by all threads
+  const bool filter = u.filter_u && b.filt;
+  if (filter)
+    for (int i = threadIdx.x; i < T * T; i += kSumBlock) sfilt[i] = b.filt[i];
   for (int i = threadIdx.x; i < TN; i += kSumBlock) {
     const int t = i / nu, d = i - t * nu;
     const int ts = u.shift ? min(t + 1, T - 1) : t;
@@ -453,10 +480,10 @@ DEV void finish_body(const UpdateCfg& u, const UpdateBufs& b, float* smean /* sh
       seq[SEQ_BEST * TN + i] = part[3 * TN + i];
     }
     float out = smean[i];
-    if (u.filter_u && b.filt) {
+    if (filter) {
       const int t = i / nu, d = i - t * nu;
       float acc = 0.0f;
-      for (int jj = 0; jj < T; ++jj) acc += b.filt[t * T + jj] * smean[jj * nu + d];
+      for (int jj = 0; jj < T; ++jj) acc += sfilt[t * T + jj] * smean[jj * nu + d];
       out = acc;
     }
     b.result[i] = out;
@@ -481,7 +508,8 @@ DEV void finish_body(const UpdateCfg& u, const UpdateBufs& b, float* smean /* sh
     }
   }
   const float mean_cost = part[6 * TN] / (float)u.Kg;
-  for (int k = threadIdx.x; k < u.K; k += kSumBlock) b.cost_total[k] = b.cost_sum[k] + mean_cost;
+  if (!(u.fuse_finish && !b.peer.n))   // (single-rank commands: written by k_wsum's cost-sum CTA)
+    for (int k = threadIdx.x; k < u.K; k += kSumBlock) b.cost_total[k] = b.cost_sum[k] + mean_cost;
   if (threadIdx.x == 0) {
     const Stats* S = b.stats;
     M3P2ICommandInfo* in = b.info;
@@ -498,12 +526,12 @@ DEV void finish_body(const UpdateCfg& u, const UpdateBufs& b, float* smean /* sh
 }
 
 __global__ void __launch_bounds__(kSumBlock) k_finish(const UpdateCfg u, const UpdateBufs b) {
-  extern __shared__ float smean[];  // [T*nu] new mean
+  extern __shared__ float smean[];  // [T*nu] new mean + [T*T] filter matrix
   finish_body(u, b, smean);
 }
 
 void launch_finish(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches) {
-  k_finish<<<1, kSumBlock, sizeof(float) * u.T * u.nu, st>>>(u, b);
+  k_finish<<<1, kSumBlock, sizeof(float) * (u.T * u.nu + u.T * u.T), st>>>(u, b);
   ++*launches;
 }
 

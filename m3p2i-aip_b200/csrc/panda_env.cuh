@@ -18,10 +18,15 @@ struct PandaEnv {
   float q[9], qd[9];
   Cube cube[2];             // cubeA, cubeB
   V3 f_table, f_shelf, f_cubeb;
+  // not part of the stored state: which cubes slept through the last sub-step this thread integrated (bit i) and on
+  // which fixed box (panda_step's dormant shortcut)
+  unsigned slept;
+  int support[2];
 
   DEV void load(const float* p, int stride, int k) {
     const float* s = p + k;
     int f = 0;
+    slept = 0u; support[0] = 0; support[1] = 0;
 #pragma unroll
     for (int j = 0; j < 9; ++j) { q[j] = s[(f++) * stride]; qd[j] = s[(f++) * stride]; }
 #pragma unroll
@@ -67,6 +72,7 @@ constexpr float kHandZ = 0.107f;             // panda_hand_joint origin (urdf:18
 constexpr float kHandYawC = 0.70710678118f;  // cos(-pi/4)
 constexpr float kHandYawS = -0.70710678118f; // sin(-pi/4)
 constexpr float kFingerZ = 0.0584f;          // panda_finger_joint1/2 origin (urdf:229,237)
+constexpr float kGripReachT = 0.12f;         // hand box centre to the farthest point of a finger box, minus the hand box radius
 
 template <int J>
 DEV void panda_joint(V3& p, M33& R, V3& v, V3& w, float qj, float qdj, bool want_twist) {
@@ -488,6 +494,32 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
         L[f].axis = mk(0, 0, 0); L[f].slide = 0.0f; L[f].ims = 0.0f;
       }
     }
+    // dormant cubes: both slept through the previous sub-step and the gripper's bounding sphere (hand + fingers, radius
+    // hand radius + kGripReachT about the hand box centre) is out of reach of either: every test below would repeat
+    // its result (nothing of the cubes moved, no link box passes its bounding-sphere test), so only the weight the
+    // supports carry is booked and the contact stage is skipped
+    bool dormant = e.slept == 3u;
+    if (dormant) {
+      const float hrad = sqrtf(dot(lbox[2].half, lbox[2].half));
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const V3 hc = mk(P.cube_half[i][0], P.cube_half[i][1], P.cube_half[i][2]);
+        const V3 dh = lbox[2].c - e.cube[i].p;
+        const float rfar = hrad + kGripReachT + sqrtf(dot(hc, hc)) + P.contact_margin;
+        dormant = dormant && dot(dh, dh) > rfar * rfar;
+      }
+    }
+    if (dormant) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float wgt = P.cube_mass[i] * P.gravity * h;
+        if (e.support[i] == P.idx_table && P.report_cube) imp_table.z -= wgt;
+        if (e.support[i] == P.idx_shelf && P.report_cube) imp_shelf.z -= wgt;
+        if (i == 1) imp_cubeb.z += wgt;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) prev[q] = 0u;
+    } else {
     OBox3 cbox[2];
     Dyn3 C[2];
 #pragma unroll
@@ -588,6 +620,10 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
     for (int q = 0; q < 4; ++q) prev[q] = cur[q];
 #pragma unroll
     for (int i = 0; i < 2; ++i) { e.cube[i].v = C[i].v; e.cube[i].w = C[i].w; }
+    e.slept = (asleep[0] ? 1u : 0u) | (asleep[1] ? 2u : 0u);
+    e.support[0] = first_box[0]; e.support[1] = first_box[1];
+    }   // not dormant
+    const bool moved[2] = {!(e.slept & 1u), !(e.slept & 2u)};
 #pragma unroll
     for (int f = 0; f < 2; ++f) {
       e.qd[7 + f] = clampf(L[f].slide, -P.qd_limit[7 + f], P.qd_limit[7 + f]);
@@ -611,7 +647,7 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      if (asleep[i]) continue;
+      if (!moved[i]) continue;
       Cube& c = e.cube[i];
       c.p = c.p + h * c.v;
       const float x = c.qx, y = c.qy, z = c.qz, w = c.qw, hh = 0.5f * h;

@@ -30,7 +30,7 @@
 namespace m3 {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr float kGripReach = 0.12f;   // hand box centre to the farthest point of a finger box, minus the hand box radius
+constexpr float kGripReach = kGripReachT;
 
 template <int CPL>
 struct TeamShape {

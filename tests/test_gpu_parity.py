@@ -342,12 +342,12 @@ def test_team_and_thread_kernels_agree(task, mm, shelf):
 
 @pytest.mark.parametrize("env,task,K,T,lanes", [
     ("panda_env", "pick", 21, 9, 0), ("panda_env", "reach", 20, 64, 0), ("point_env", "push", 33, 64, 0),
-    ("point_env", "navigation", 20, 9, 0), ("panda_env", "place", 4609, 12, 0), ("panda_env", "place", 8289, 9, 0),
+    ("point_env", "navigation", 20, 9, 0), ("panda_env", "place", 4609, 12, 0), ("panda_env", "place", 8289, 9, 0), ("panda_env", "place", 12433, 9, 0),
     ("panda_env", "pick", 21, 9, 8), ("panda_env", "reach", 23, 12, 8), ("panda_env", "pick", 2073, 9, 0),
     ("panda_env", "reach", 4145, 9, 0)])
 def test_edge_sizes(env, task, K, T, lanes):
     """Ragged sizes: K below one warp / not a multiple of a team, a warp or a CTA for every rollout kernel shape (16
-    lanes up to K = 2072, 8 lanes with one CTA per SM up to 4144 and with two up to 8288, thread per sample beyond;
+    lanes up to K = 2072, 8 lanes in one / two / three waves of 4144 samples up to 12432, thread per sample beyond;
     lanes = 8 forced at tiny K), the minimum K (20, top-k) and T (9, Savitzky-Golay window), the maximum horizon (64)."""
     O.set_threads(8)
     case = ("edge", env, task, [-1.0, -1.0] if env == "point_env" else None, K, T, False, False, [0.2, 2.45] if task == "push" else None)
@@ -368,6 +368,6 @@ def test_edge_sizes(env, task, K, T, lanes):
         assert_close(a_n, a_o, 1e-2, 1e-2, f"action [{i}]")
         assert np.isfinite(c_n).all()
         if env == "panda_env":
-            assert info.rollout_lanes == (lanes or (16 if K <= 2072 else 8 if K <= 8288 else 1))
+            assert info.rollout_lanes == (lanes or (16 if K <= 2072 else 8 if K <= 12432 else 1))
     o.close()
     n.close()
