@@ -155,7 +155,7 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-NCU_SUMMARY = {"c4": "r02_ncu_rollout_team_c4_summary.csv"}
+NCU_SUMMARY = {"c4": "r02_ncu_rollout_team_c4_summary.csv", "c4_grasp": "r02_ncu_rollout_team_grasp_summary.csv"}
 
 
 def ncu_numbers(name):
