@@ -455,7 +455,7 @@ def main():
                        "timing": "CUDA events per step on the launching stream, max over ranks per step; value from the mean over steps"},
             "e2e": {"value": Kg * T / e2e_s, "unit": "sample-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
-                    "api": "NativePlanner.set_state + command (m3p2i_set_state / m3p2i_command), host arrays"},
+                    "api": "NativePlanner.set_state + command (m3p2i_set_state / m3p2i_command), host arrays in and out; the start state rides in the kernel parameters of the rollout launch, the action and info rows are written by the update kernel into mapped pinned host memory (no separate copies), the call returns after a stream synchronize"},
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
             "clocks": clocks,

@@ -116,7 +116,9 @@ struct M3P2IHandle_ {
   // uploaded lazily (it must survive a reallocation of the result buffer)
   float* pin = nullptr;
   size_t pin_n = 0;
-  float* pin_base = nullptr;   // [64]
+  float* pin_base = nullptr;   // [64] packed start state (host staging)
+  float* mirror = nullptr;     // mapped pinned host memory: [2 T nu] result rows + M3P2ICommandInfo, written by the kernels
+  float* mirror_dev = nullptr; // its device address
   M3P2ICommandInfo last_info;
   // multi-GPU
   ncclComm_t comm = nullptr;
@@ -204,12 +206,15 @@ int ensure_env(H* h) {
   return 0;
 }
 
+int upload_base(H* h);
+
 // broadcast the set_state state into the K persistent envs
 int materialize(H* h) {
   if (h->env_live) return 0;
   if (!h->have_state) return fail(M3P2I_ERR_STATE, "set_state has not been called");
   int rc = ensure_env(h);
   if (rc) return rc;
+  if ((rc = upload_base(h))) return rc;
   launch_sim_reset(h->cfg.env_type, h->base.p, h->env.p, h->cfg.num_samples, h->stream);
   CK(cudaGetLastError());
   h->env_live = true;
@@ -254,6 +259,7 @@ RolloutCfg make_rcfg(const H* h) {
   memcpy(r.sigma, c.sigma, sizeof(r.sigma));
   memcpy(r.goal, h->goal, sizeof(r.goal));
   r.seed_lo = (uint32_t)c.seed; r.seed_hi = (uint32_t)(c.seed >> 32);
+  if (h->pin_base) memcpy(r.base_env, h->pin_base, sizeof(r.base_env));
   return r;
 }
 
@@ -261,7 +267,7 @@ RolloutBufs make_rbufs(const H* h) {
   RolloutBufs b;
   b.noise = h->have_noise ? h->noise.p : nullptr;
   b.noise_row0 = h->have_row0 ? h->noise_row0.p : nullptr;
-  b.seq = h->seq.p; b.actions_in = nullptr; b.base = h->base.p;
+  b.seq = h->seq.p; b.actions_in = nullptr;
   b.sigma_dev = h->cfg.update_cov ? h->stats.p->sigma : nullptr; b.env = h->env.p; b.vel_target = h->vel_target.p;
   b.actions = h->actions.p; b.states = h->states.p; b.cost_h = h->cost_h.p; b.J = h->J.p; b.cost_sum = h->cost_sum.p;
   b.refs = nullptr;
@@ -326,6 +332,8 @@ UpdateBufs make_ubufs(const H* h) {
   b.J_global = h->J_global.p; b.weights = h->weights.p; b.stats = h->stats.p; b.actions = h->actions.p;
   b.cost_sum = h->cost_sum.p; b.partials = h->partials.p; b.seq = h->seq.p; b.filt = h->have_filt ? h->filt.p : nullptr;
   b.cost_total = h->cost_total.p; b.result = h->result.p; b.info = h->info.p;
+  b.host_result = h->mirror_dev;
+  b.host_info = h->mirror_dev ? reinterpret_cast<M3P2ICommandInfo*>(h->mirror_dev + 2 * (size_t)h->cfg.horizon * h->cfg.nu) : nullptr;
   b.done_counter = h->ref_flags.p + 2;
   b.stats_scratch = h->ref_flags.p + 8;
   memset(&b.peer, 0, sizeof(b.peer));
@@ -352,15 +360,15 @@ int upload_base(H* h) {
   if (!h->base_dirty) return 0;
   // h->pin_base[0..nf) holds the packed base env (written by set_state)
   CK(cudaMemcpyAsync(h->base.p, h->pin_base, sizeof(float) * h->nf, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));   // set_state may rewrite the staging slot right away (sim facade path only)
   h->base_dirty = false;
   return 0;
 }
 
 // phase 1: sample + rollout of the local shard; J of the local shard lands in h->J (and, single rank, J_global)
 int run_rollout(H* h, int* launches, const float* actions_in_dev, bool push_peers = false) {
-  int rc = upload_base(h);
-  if (rc) return rc;
-  RolloutCfg c = make_rcfg(h);
+  int rc = 0;
+  RolloutCfg c = make_rcfg(h);   // carries the start state (base_env): no upload
   RolloutBufs b = make_rbufs(h);
   const bool refs = needs_refs(h);
   if (actions_in_dev) { c.open_loop = 1; b.actions_in = actions_in_dev; }
@@ -431,9 +439,12 @@ int fetch(H* h, float* out_action, float* out_cost_total, M3P2ICommandInfo* info
   int rc = ensure_pin(h, std::max<size_t>(need, 256));
   if (rc) return rc;
   float* p = h->pin;
-  CK(cudaMemcpyAsync(p, h->result.p, sizeof(float) * 2 * TN, cudaMemcpyDeviceToHost, h->stream));
   M3P2ICommandInfo* pi = reinterpret_cast<M3P2ICommandInfo*>(p + 2 * TN);
-  CK(cudaMemcpyAsync(pi, h->info.p, sizeof(M3P2ICommandInfo), cudaMemcpyDeviceToHost, h->stream));
+  const bool mirrored = h->mirror != nullptr;   // the update kernels wrote both straight into mapped host memory
+  if (!mirrored) {
+    CK(cudaMemcpyAsync(p, h->result.p, sizeof(float) * 2 * TN, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(pi, h->info.p, sizeof(M3P2ICommandInfo), cudaMemcpyDeviceToHost, h->stream));
+  }
   float* pc = p + 2 * TN + sizeof(M3P2ICommandInfo) / sizeof(float) + 1;
   if (out_cost_total) CK(cudaMemcpyAsync(pc, h->cost_total.p, sizeof(float) * K, cudaMemcpyDeviceToHost, h->stream));
   unsigned* perr = reinterpret_cast<unsigned*>(p + 2 * TN + sizeof(M3P2ICommandInfo) / sizeof(float));
@@ -445,6 +456,10 @@ int fetch(H* h, float* out_action, float* out_cost_total, M3P2ICommandInfo* info
     CK(cudaMemsetAsync(h->ref_flags.p + 4, 0, sizeof(unsigned), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return fail(M3P2I_ERR_STATE, "peer exchange timed out: a rank did not deliver its costs / partial sums");
+  }
+  if (mirrored) {
+    p = h->mirror;
+    pi = reinterpret_cast<M3P2ICommandInfo*>(h->mirror + 2 * TN);
   }
   if (out_action) memcpy(out_action, unfiltered ? p + TN : p, sizeof(float) * TN);
   if (out_cost_total) memcpy(out_cost_total, pc, sizeof(float) * K);
@@ -591,6 +606,21 @@ int m3p2i_create(const M3P2IConfig* cfg, int device, m3p2i_handle* out) {
     m3p2i_destroy(h);
     return fail(M3P2I_ERR_CUDA, "m3p2i_create: cudaMallocHost failed");
   }
+  memset(h->pin_base, 0, sizeof(float) * 64);
+  {
+    // result rows + info as the kernels write them, readable by the host right after the stream sync
+    const size_t bytes = sizeof(float) * 2 * (size_t)cfg->horizon * cfg->nu + sizeof(M3P2ICommandInfo);
+    void* dev = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h->mirror), bytes, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&dev, h->mirror, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (h->mirror) cudaFreeHost(h->mirror);
+      h->mirror = nullptr;   // fall back to D2H copies
+    } else {
+      memset(h->mirror, 0, bytes);
+      h->mirror_dev = static_cast<float*>(dev);
+    }
+  }
   *out = h;
   return 0;
 }
@@ -609,6 +639,7 @@ void m3p2i_destroy(m3p2i_handle h) {
   h->refs.release(); h->ref_flags.release(); h->stats.release(); h->info.release();
   if (h->pin) cudaFreeHost(h->pin);
   if (h->pin_base) cudaFreeHost(h->pin_base);
+  if (h->mirror) cudaFreeHost(h->mirror);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->evr) cudaEventDestroy(h->evr);
@@ -673,8 +704,7 @@ int m3p2i_set_state(m3p2i_handle h, const float* dof, const float* root) {
       }
     }
   }
-  // the staging slot may still be in flight from the previous tick
-  CK(cudaStreamSynchronize(h->stream));
+  // (the staging slot is read on the host when a launch is prepared, or uploaded synchronously by the sim facade)
   pack_env(h, dof, root, h->pin_base);
   h->base_dirty = true;
   h->have_state = true;

@@ -79,6 +79,9 @@ struct RolloutCfg {
   float u_min[kMaxNu], u_max[kMaxNu], sigma[kMaxNu];
   float goal[8];
   uint32_t seed_lo, seed_hi;
+  // the packed start state (one env, field-major: m3p2i_set_state) travels with the launch: no H2D copy per command,
+  // and every thread reads it from the constant bank
+  float base_env[56];
 };
 
 // values of sample 0 / sample K/2 of the global batch read by every sample's reach cost
@@ -123,7 +126,6 @@ struct RolloutBufs {
   const float* seq;        // [SEQ_COUNT][T*nu] planner sequences (un-shifted; the kernel reads them shifted)
   const float* actions_in; // [T][nu][K] open-loop actions or nullptr
   const float* sigma_dev;  // [nu] adapted noise scale (update_cov) or nullptr: use RolloutCfg::sigma
-  const float* base;       // one env, field-major (broadcast start state)
   float* env;              // [fields][K] persistent envs
   float* vel_target;       // [nu][K]
   float* actions;          // [T][nu][K]

@@ -47,7 +47,7 @@ DEV void produce_refs<PandaParams>(const RolloutCfg& c, const PandaParams& P, co
   const int kl = (kg >= c.offset && kg < c.offset + c.K) ? kg - c.offset : -1;
   PandaEnv e;
   if (c.env_live && kl >= 0) e.load(b.env, c.K, kl);
-  else e.load(b.base, 1, 0);
+  else e.load(c.base_env, 1, 0);
   float u[9];
   for (int t = 0; t < c.T; ++t) {
     sample_action<9>(c, b, kg, kl, t, u);
@@ -72,7 +72,7 @@ k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename
   const int K = c.K, kg = c.offset + k;
   Env e;
   if (c.env_live) e.load(b.env, K, k);
-  else e.load(b.base, 1, 0);
+  else e.load(c.base_env, 1, 0);
   float run = 0.0f, J = 0.0f, g = 1.0f;
   float u[NU];
   for (int t = 0; t < c.T; ++t) {
@@ -488,6 +488,7 @@ DEV void finish_body(const UpdateCfg& u, const UpdateBufs& b, float* smean /* sh
     }
     b.result[i] = out;
     b.result[TN + i] = smean[i];
+    if (b.host_result) { b.host_result[i] = out; b.host_result[TN + i] = smean[i]; }
   }
   if (u.update_cov && !u.multi_modal) {
     // mppi.py:505-516: delta = actions - NEW mean; cov_update_d = mean_t sum_k w_k delta_ktd^2 from the moments
@@ -522,6 +523,7 @@ DEV void finish_body(const UpdateCfg& u, const UpdateBufs& b, float* smean /* sh
     in->mean_cost_sum = mean_cost;
     in->beta_iters = S->beta_iters;
     in->peer_wait_ms[0] = S->peer_wait_ms[0]; in->peer_wait_ms[1] = S->peer_wait_ms[1];
+    if (b.host_info) *b.host_info = *in;
   }
 }
 

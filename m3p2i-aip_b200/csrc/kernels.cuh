@@ -39,6 +39,8 @@ struct UpdateBufs {
   float* cost_total;       // [K]
   float* result;           // [T*nu] filtered action, followed by [T*nu] unfiltered mean
   M3P2ICommandInfo* info;  // device copy
+  float* host_result;      // the same two rows in mapped pinned host memory (written by the kernel: no D2H copy)
+  M3P2ICommandInfo* host_info;
   unsigned* done_counter;  // CTA completion counter of the fused wsum + finish launch
   unsigned* stats_scratch; // [0] CTA completion counter of the multi-modal k_stats, [1..3] beta iterations per set
   PeerReduce peer;

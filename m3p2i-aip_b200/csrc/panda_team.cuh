@@ -399,7 +399,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
 
   TeamEnv e;
   if (c.env_live && k >= 0) e.load(b.env, K, k, g);
-  else e.load(b.base, 1, 0, g);
+  else e.load(c.base_env, 1, 0, g);
   float run = 0.0f, J = 0.0f, gam = 1.0f;
   // group-partial impulse sums (identical in the lanes of a group), lane-partial penalty sums, per step
   V3 imp_table = mk(0, 0, 0), imp_shelf = mk(0, 0, 0), imp_cubeb = mk(0, 0, 0), pen = mk(0, 0, 0);

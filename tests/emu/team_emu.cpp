@@ -107,7 +107,7 @@ int emu_team_rollout_actions(const M3P2IConfig* cfg, const M3P2IPandaScene* scen
     for (int j = 0; j < T * NU; ++j) act_in[(size_t)j * K + k] = actions[(size_t)k * T * NU + j];
   RolloutBufs b;
   memset(&b, 0, sizeof(b));
-  b.seq = seq.data(); b.actions_in = act_in.data(); b.base = base.data(); b.env = env.data(); b.vel_target = vel.data();
+  b.seq = seq.data(); b.actions_in = act_in.data(); memcpy(c.base_env, base.data(), sizeof(c.base_env)); b.env = env.data(); b.vel_target = vel.data();
   b.actions = act.data(); b.states = states.data(); b.cost_h = cost_h.data(); b.J = J.data(); b.cost_sum = cost_sum.data();
   b.refs = refs ? ref_buf.data() : nullptr; b.ref_flags = flags;
 
