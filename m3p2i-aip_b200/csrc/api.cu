@@ -744,6 +744,8 @@ int m3p2i_set_noise_halton_spline(m3p2i_handle h, int knot_scale, int degree, fl
                                   int perm_stride) {
   if (!h) return fail(M3P2I_ERR_ARG, "null handle");
   const int K = h->cfg.num_samples, T = h->cfg.horizon, nu = h->cfg.nu;
+  if (h->cfg.noise_mode != M3P2I_NOISE_TABLE)
+    return fail(M3P2I_ERR_STATE, "the halton-spline table needs noise_mode = M3P2I_NOISE_TABLE (this planner samples in the kernel)");
   if (knot_scale < 1 || degree < 1 || degree > 3) return fail(M3P2I_ERR_ARG, "knot_scale >= 1 and degree 1..3 expected");
   const int m = T / knot_scale, ndims = m * nu;
   if (m <= degree) return fail(M3P2I_ERR_ARG, "horizon / knot_scale must exceed the spline degree (the reference YAMLs: horizon >= 12)");

@@ -118,3 +118,7 @@ def test_device_rejects_bad_arguments():
         n.set_noise_halton_spline(perms=np.zeros((27, 50), np.uint16))    # stride below the largest base (103)
     n.set_noise_halton_spline()
     n.close()
+    ph = make_backend(native.NativePlanner, cfg, noise_mode=A.NOISE_PHILOX)
+    with pytest.raises(native.NativeError):
+        ph.set_noise_halton_spline()                                       # in-kernel sampling: a table would be ignored
+    ph.close()
