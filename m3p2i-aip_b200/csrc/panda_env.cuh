@@ -494,19 +494,21 @@ DEV void panda_step(PandaEnv& e, const PandaParams& P, const float* u, float dt,
         L[f].axis = mk(0, 0, 0); L[f].slide = 0.0f; L[f].ims = 0.0f;
       }
     }
-    // dormant cubes: both slept through the previous sub-step and the gripper's bounding sphere (hand + fingers, radius
-    // hand radius + kGripReachT about the hand box centre) is out of reach of either: every test below would repeat
-    // its result (nothing of the cubes moved, no link box passes its bounding-sphere test), so only the weight the
-    // supports carry is booked and the contact stage is skipped
+    // dormant cubes: both slept through the previous sub-step and no link box comes within the sum of the bounding radii
+    // (+ margin) of either: every test below would repeat its result (nothing of the cubes moved, boxes_near fails for
+    // every link), so only the weight the supports carry is booked and the contact stage is skipped
     bool dormant = e.slept == 3u;
     if (dormant) {
-      const float hrad = sqrtf(dot(lbox[2].half, lbox[2].half));
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const V3 hc = mk(P.cube_half[i][0], P.cube_half[i][1], P.cube_half[i][2]);
-        const V3 dh = lbox[2].c - e.cube[i].p;
-        const float rfar = hrad + kGripReachT + sqrtf(dot(hc, hc)) + P.contact_margin;
-        dormant = dormant && dot(dh, dh) > rfar * rfar;
+        const float rc = sqrtf(dot(hc, hc)) + P.contact_margin;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {   // the bounding-sphere part of boxes_near(lbox[f], cbox[i]): a superset of lnear
+          const V3 dl = lbox[f].c - e.cube[i].p;
+          const float rr = sqrtf(dot(lbox[f].half, lbox[f].half)) + rc;
+          dormant = dormant && dot(dl, dl) > rr * rr;
+        }
       }
     }
     if (dormant) {

@@ -600,16 +600,22 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     const V3 hhalf = mk(P.hand_half[0], P.hand_half[1], P.hand_half[2]);
     float slide[2] = {e.qd[7], e.qd[8]};
     // ---- dormant cubes: a cube that slept through the previous sub-step (velocity zero, supported, nothing near) and
-    // whose distance to the gripper exceeds the bounding sphere of hand + fingers plus its own radius and the contact
-    // margin sleeps through this one too -- every test of the full path below would come out as before (nothing of the
-    // cube moved, no link box can pass its centre-distance pre-test). When that holds for every cube of the warp, all
-    // the cube work of the sub-step is skipped; only the weight the support carries is booked.
+    // that none of the three link boxes can reach (their centre-distance pre-tests of the full path fail) sleeps through
+    // this one too -- every test of the full path below would come out as before (nothing of the cube moved). When that
+    // holds for every cube of the warp, all the cube work of the sub-step is skipped; only the weight the support
+    // carries is booked.
     bool asleep = true;
     bool dormant;
     {
-      const V3 dh = lc[2] - e.cu.p;
-      const float rfar = hrad + kGripReach + rad_own + P.contact_margin;
-      dormant = was_asleep && dot(dh, dh) > rfar * rfar;
+      // the centre-distance pre-tests of the full path (see lnear below), all three failing
+      const V3 d2 = lc[2] - e.cu.p;
+      const float rf = frad + rad_own + P.contact_margin, rh = hrad + rad_own + P.contact_margin;
+      const float rfar = rh + kGripReach, dd2 = dot(d2, d2);
+      dormant = was_asleep && dd2 > rh * rh;
+      if (dormant && !(dd2 > rfar * rfar)) {   // inside the gripper's bounding sphere: the two finger boxes decide
+        const V3 d0 = lc[0] - e.cu.p, d1 = lc[1] - e.cu.p;
+        dormant = dot(d0, d0) > rf * rf && dot(d1, d1) > rf * rf;
+      }
     }
     if (__all_sync(kFull, dormant)) {
       const float wgt = P.cube_mass[g] * P.gravity * h;   // the support carries the weight
