@@ -966,12 +966,16 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     }
     return;
   }
-  if (defer_reach && t.tl == 0) {
+  if (defer_reach) {
     // the T reach costs, now that the rows of the batch they read are published: ONE wait for the producer's last
-    // step (flags count steps), then refs[0..T) are plain loads
-    (void)ref_wait(b, T - 1, c.epoch, c.multi_modal != 0);
-#pragma unroll 4
-    for (int ps = 0; ps < T; ++ps) {
+    // step (flags count steps), then refs[0..T) are plain loads. The lanes of a team share the steps (lane l takes
+    // steps l, l + TM, ...: cost ingredients from shared memory, the row of the batch from L2) and add up their parts.
+    if (t.tl == 0) (void)ref_wait(b, T - 1, c.epoch, c.multi_modal != 0);
+    __syncwarp();
+    float g_l = 1.0f, g_stride = 1.0f, run_l = 0.0f, J_l = 0.0f;
+    for (int q = 0; q < TM; ++q) { if (q < t.tl) g_l *= c.gamma; g_stride *= c.gamma; }
+#pragma unroll 2
+    for (int ps = t.tl; ps < T; ps += TM) {
       PandaRef ref;
       ref.cube0[0] = __ldcg(&b.refs[ps].cube0[0]); ref.cube0[1] = __ldcg(&b.refs[ps].cube0[1]);
       ref.cube0[2] = __ldcg(&b.refs[ps].cube0[2]); ref.sel_axis = __ldcg(&b.refs[ps].sel_axis);
@@ -979,11 +983,18 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       ReachParts rp;
       rp.ee = mk(p0.x, p0.y, p0.z); rp.min_y = p0.w; rp.dz = mk(p1.x, p1.y, p1.z);
       const float cost = reach_combine(rp, c, kg, ref);
-      run += cost;
-      J += gam * cost;
-      gam *= c.gamma;
-      if (writer) b.cost_h[(size_t)ps * K + k] = cost;
+      run_l += cost;
+      J_l += g_l * cost;
+      g_l *= g_stride;
+      if (valid) b.cost_h[(size_t)ps * K + k] = cost;
     }
+#pragma unroll
+    for (int o = TM / 2; o > 0; o >>= 1) {
+      run_l += __shfl_xor_sync(kFull, run_l, o);
+      J_l += __shfl_xor_sync(kFull, J_l, o);
+    }
+    run += run_l;
+    J += J_l;
   }
   if (writer) { b.cost_sum[k] = run; publish_J(b, c, k, J); }
   if (c.store_env) {
