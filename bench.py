@@ -380,6 +380,7 @@ def main():
         wait_p.append(info.peer_wait_ms[1])
     last = planner.command_resident(sync=True)
     launches_per_step, lanes = last.launches, int(last.rollout_lanes)
+    beta_iters = int(last.beta_iters)
     barrier()
 
     # ---------------- end to end through the public API with host buffers (H2D state in, D2H action out)
@@ -458,6 +459,7 @@ def main():
                     "api": "NativePlanner.set_state + command (m3p2i_set_state / m3p2i_command), host arrays in and out; the start state rides in the kernel parameters of the rollout launch, the action and info rows are written by the update kernel into mapped pinned host memory (no separate copies), the call returns after a stream synchronize"},
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
+            "beta_search_iterations": beta_iters,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,

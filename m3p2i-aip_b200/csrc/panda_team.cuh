@@ -508,9 +508,12 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
           if (qn < lo_o) { qn = lo_o; vo = 0.0f; }
           if (qn > up_o) { qn = up_o; vo = 0.0f; }
           qo = qn;
-          // state row of a finished step: (q1, qd1) from lane 0, (q2, qd2) from lane 1 (reactive_tamp.py:66-69)
-          if (valid && t.tl < 2 && si == ns - 1)
-            reinterpret_cast<float2*>(b.states + (size_t)stepi * K + k)[t.tl] = make_float2(qo, vo);
+          // state row of a finished step (q1, qd1, q2, qd2; reactive_tamp.py:66-69): lane 0 owns joint 1 and fetches
+          // joint 2 from lane 1, so every sample stores ONE float4 and the samples of a warp one contiguous segment
+          if (si == ns - 1) {
+            const float q2 = __shfl_sync(kFull, qo, t.team_base + 1), v2 = __shfl_sync(kFull, vo, t.team_base + 1);
+            if (writer) b.states[(size_t)stepi * K + k] = make_float4(qo, vo, q2, v2);
+          }
         }
       }
       fk_from_sincos(P, ssn, scs, sqd, Hl);
