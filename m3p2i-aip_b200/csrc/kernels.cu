@@ -90,7 +90,15 @@ k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename
     b.cost_h[(size_t)t * K + k] = cost;
   }
   b.cost_sum[k] = run;
-  publish_J(b, c, k, J);
+  b.J[k] = J;
+  if (b.peer.n) {
+#ifndef M3_EMU
+    push_J_store(b.peer, c.offset, k, J);
+    const unsigned m = __activemask();   // the lanes of this warp that own a sample
+    __syncwarp(m);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) push_J_commit(b.peer, K, (unsigned)__popc(m));
+#endif
+  }
   if (c.store_env) {
     e.store(b.env, K, k);
 #pragma unroll

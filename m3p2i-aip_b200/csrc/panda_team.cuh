@@ -999,7 +999,11 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     run += run_l;
     J += J_l;
   }
-  if (writer) { b.cost_sum[k] = run; publish_J(b, c, k, J); }
+  if (writer) {
+    b.cost_sum[k] = run;
+    b.J[k] = J;
+    if (b.peer.n) push_J_store(b.peer, c.offset, k, J);   // committed per CTA in team_kernel_body
+  }
   if (c.store_env) {
     // arm joints back from their owner lanes (warp-uniform branch: every team of the launch stores or none does)
 #pragma unroll
@@ -1031,6 +1035,15 @@ DEV void team_kernel_body(const RolloutCfg& c, const PandaParams& P, const Rollo
     k = (kg >= c.offset && kg < c.offset + c.K) ? kg - c.offset : -1;
   }
   team_rollout<CPL>(c, P, b, t, k, kg, valid, producer, which);
+  if (b.peer.n && !producer) {
+    // sharded over peer memory: the CTA's J values are in every mailbox; one thread orders them and counts them in
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int first = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x) / TM;
+      const int cnt = min((int)blockDim.x / TM, c.K - first);
+      if (cnt > 0) push_J_commit(b.peer, c.K, (unsigned)cnt);
+    }
+  }
 }
 
 }  // namespace m3

@@ -105,20 +105,22 @@ DEV PandaRef ref_wait(const RolloutBufs& b, int t, unsigned epoch, bool two) {
 }
 
 // ------------------------------------------------------------------ all-gather of J fused into the rollout
-// Called by the one thread that owns sample k once its rollout is complete. System-scope fences order the remote
-// stores before the ticket and the ticket before the flags, so a peer that sees jflag == epoch sees every J.
-DEV void push_J(const PeerPush& p, int K, int offset, int k, float J) {
+// The thread that owns sample k stores its J into Jg[offset + k] of EVERY mailbox once its rollout is complete
+// (push_J_store: plain remote stores). ONE thread per warp (thread-per-sample kernel) or per CTA (team kernel) then
+// commits them after a barrier that orders its companions' stores before it: a system-scope fence, the arrival count on
+// the rank's ticket, and -- by whoever completes the K arrivals -- the flags in every mailbox. A peer that sees
+// jflag == epoch therefore sees every J. (One fence and one atomic per warp / CTA instead of one per sample: at
+// K = 4096 that took 8 - 17 us out of a sharded rollout.)
+DEV void push_J_store(const PeerPush& p, int offset, int k, float J) {
   for (int r = 0; r < p.n; ++r) p.Jg[r][offset + k] = J;
+}
+DEV void push_J_commit(const PeerPush& p, int K, unsigned count) {
   __threadfence_system();
-  if (atomicAdd(p.ticket, 1u) == (unsigned)K - 1u) {
+  if (atomicAdd(p.ticket, count) == (unsigned)K - count) {
     *p.ticket = 0u;   // the next launch on this stream starts from zero
     __threadfence_system();
     for (int r = 0; r < p.n; ++r) *(volatile unsigned*)(p.jflag[r] + p.rank) = p.epoch;
   }
-}
-DEV void publish_J(const RolloutBufs& b, const RolloutCfg& c, int k, float J) {
-  b.J[k] = J;
-  if (b.peer.n) push_J(b.peer, c.K, c.offset, k, J);
 }
 
 // Threads 0..n-1 of the CTA poll one flag each until it reaches `epoch`; bounded, so that a peer that died cannot
