@@ -324,6 +324,7 @@ UpdateCfg make_ucfg(const H* h, int shift) {
   u.gamma = c.gamma; u.step_size_mean = c.step_size_mean;
   u.fuse_finish = 0;
   u.update_cov = c.update_cov && !c.multi_modal;
+  u.stage_J = 0;
   return u;
 }
 

@@ -288,12 +288,18 @@ __global__ void __launch_bounds__(kStatsBlock) k_stats(const UpdateCfg u, const 
   // (the weight rows are zero outside the ranges written below: cleared once at allocation, the ranges never change)
   {
     const int lo = s == 2 ? half : 0, n = s == 0 ? Kg : (s == 1 ? half : Kg - half);
+    // the set's costs are read three or more times (minimum, one exp-sum per beta of the search, weights): stage them
+    // in shared memory on the first pass when they fit (u.stage_J: the launch reserved 4 Kg bytes)
+    extern __shared__ float sJ[];
+    const bool staged = u.stage_J != 0;
     float v = INFINITY;
     int vi = 0x7fffffff;
     for (int i = threadIdx.x; i < n; i += kStatsBlock) {
       const float x = J[lo + i];
+      if (staged) sJ[i] = x;
       if (x < v) { v = x; vi = i; }
     }
+    if (staged) J = sJ - lo;   // J[lo + i] below reads the staged copy (made visible by block_argmin's barriers)
     float jmin; int imin;
     block_argmin<kStatsBlock>(v, vi, shv, shi, jmin, imin);
     if (imin == 0x7fffffff) { imin = 0; jmin = J[lo]; }  // all-NaN / all-inf costs
@@ -357,7 +363,14 @@ __global__ void __launch_bounds__(kStatsBlock) k_stats(const UpdateCfg u, const 
 }
 
 void launch_stats(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches) {
-  launch_pdl(k_stats, dim3(u.multi_modal ? 3 : 1), dim3(kStatsBlock), 0, st, u, b);
+  // dynamic shared memory: the costs of the largest set, when they fit beside the reduction scratch
+  static bool attr_set = false;
+  constexpr size_t kStageMax = 200 * 1024;
+  if (!attr_set) { cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageMax); attr_set = true; }
+  UpdateCfg us = u;
+  const size_t bytes = sizeof(float) * (size_t)u.Kg;
+  us.stage_J = bytes <= kStageMax ? 1 : 0;
+  launch_pdl(k_stats, dim3(u.multi_modal ? 3 : 1), dim3(kStatsBlock), us.stage_J ? bytes : 0, st, us, b);
   ++*launches;
 }
 

@@ -8,6 +8,7 @@ struct UpdateCfg {
   int K, T, nu, Kg, offset, multi_modal, env_type, filter_u, shift;
   int fuse_finish;   // k_wsum's last CTA also runs the finish step (no exchange between them: single rank)
   int update_cov;    // adapt the per-dimension noise variance (mppi.py:508-516; single-mode only)
+  int stage_J;       // k_stats keeps the costs of its weight set in shared memory (set by launch_stats)
   float gamma, step_size_mean;
 };
 
