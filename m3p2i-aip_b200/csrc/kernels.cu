@@ -403,6 +403,25 @@ __global__ void __launch_bounds__(kSumBlock) k_wsum(const UpdateCfg u, const Upd
   const float* w1 = b.weights + (size_t)Kg + u.offset;
   const float* w2 = b.weights + 2 * (size_t)Kg + u.offset;
   float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, sq = 0.0f;
+  if (((K | u.offset | Kg) & 3) == 0) {
+    // 128-bit loads, all of a thread's requests in flight at once (the plane and the weights are L2-resident: the loop
+    // is bound by load latency, not bandwidth)
+    const float4* p4 = reinterpret_cast<const float4*>(plane);
+    const float4* w04 = reinterpret_cast<const float4*>(w0);
+    const float4* w14 = reinterpret_cast<const float4*>(w1);
+    const float4* w24 = reinterpret_cast<const float4*>(w2);
+#pragma unroll 4
+    for (int q = threadIdx.x; q < K / 4; q += kSumBlock) {
+      const float4 a = p4[q], w = w04[q];
+      s0 += w.x * a.x; s0 += w.y * a.y; s0 += w.z * a.z; s0 += w.w * a.w;
+      sq += w.x * a.x * a.x; sq += w.y * a.y * a.y; sq += w.z * a.z * a.z; sq += w.w * a.w * a.w;
+      if (u.multi_modal) {
+        // (half is a multiple of 4 here: a float4 never straddles the mode boundary)
+        if (u.offset + 4 * q < half) { const float4 v = w14[q]; s1 += v.x * a.x; s1 += v.y * a.y; s1 += v.z * a.z; s1 += v.w * a.w; }
+        else { const float4 v = w24[q]; s2 += v.x * a.x; s2 += v.y * a.y; s2 += v.z * a.z; s2 += v.w * a.w; }
+      }
+    }
+  } else {
   for (int k = threadIdx.x; k < K; k += kSumBlock) {
     const float a = plane[k];
     s0 += w0[k] * a;
@@ -411,6 +430,7 @@ __global__ void __launch_bounds__(kSumBlock) k_wsum(const UpdateCfg u, const Upd
       if (u.offset + k < half) s1 += w1[k] * a;
       else s2 += w2[k] * a;
     }
+  }
   }
   s0 = block_sum<kSumBlock>(s0, sh);
   if (u.multi_modal) { s1 = block_sum<kSumBlock>(s1, sh); s2 = block_sum<kSumBlock>(s2, sh); }
