@@ -11,13 +11,21 @@ from m3p2i_b200 import _abi as A, native, scene as S  # noqa: E402
 import bench  # noqa: E402
 
 
-def panda(K, T, task, lanes=0, mm=False, K_local=None, offset=0, noise=A.NOISE_PHILOX):
+GRASP_Q = [-0.21448, 1.040633, -0.091726, -1.527796, 0.144743, 2.56178, 0.807333, 0.027, 0.027]   # fingers on cubeA
+
+
+def panda(K, T, task, lanes=0, mm=False, K_local=None, offset=0, noise=A.NOISE_PHILOX, grasp=False):
     cfg = S.make_cfg("panda_env", task, None, K, T, multi_modal=mm)
     cfg.mppi.lanes_per_sample = lanes
     c = S.build_config(cfg, num_samples_local=K_local or K, sample_offset=offset, noise_mode=noise, seed=1)
     p = native.NativePlanner(c, S.build_panda_scene())
     p.set_filter_matrix(S.savgol_matrix(T))
     dof, root, goal = bench.scene_inputs()
+    if grasp:   # contact-rich: link / cube contact records, accumulators, warm start
+        dof = dof.copy()
+        dof[0::2] = GRASP_Q
+    if noise == A.NOISE_TABLE:
+        p.set_noise_halton_spline()   # the table is built on the device (k_halton_spline)
     p.set_state(dof, root)
     p.set_objective(task, goal if task == "pick" else np.zeros(7, np.float32), "close" if task == "pick" else "open")
     return p
@@ -38,6 +46,9 @@ def point(K, T, task, goal, mm=False):
 for name, p in (("pick 16 lanes", panda(64, 9, "pick")), ("pick 8 lanes", panda(44, 9, "pick", lanes=8)),
                 ("reach mm 8 lanes + producer", panda(48, 9, "reach", lanes=8, mm=True)),
                 ("pick thread per sample", panda(40, 9, "pick", lanes=1)),
+                ("grasp state 8 lanes, halton table", panda(44, 12, "pick", lanes=8, grasp=True, noise=A.NOISE_TABLE)),
+                ("grasp state 16 lanes", panda(30, 9, "pick", lanes=16, grasp=True)),
+                ("grasp state thread per sample", panda(40, 9, "pick", lanes=1, grasp=True)),
                 ("push_pull mm", point(64, 12, "push_pull", [-3.75, -3.75], mm=True))):
     a, c, info = p.command()
     assert np.isfinite(a).all() and np.isfinite(c).all(), name
