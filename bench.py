@@ -429,6 +429,34 @@ def main():
                        "note": "same workload, one GPU, K = K_per_gpu unsharded, measured on rank 0 after the sharded run"}
             solo.close()
         barrier()
+    # N > 1 with the default workload (c5): the driver's N = 1 line is the N = 1 default (c4, pick). Time that workload
+    # sharded over these N GPUs too, so that a cross-N ratio of like with like can be read from the lines the driver has
+    n1_default = None
+    if world > 1 and args.config is None and name != "c4":
+        conf4 = CONFIGS["c4"]
+        p4, ex4, _, _ = build_planner(conf4, world, rank, local_rank, args.exchange)
+        p4.set_stream(stream.cuda_stream)
+        for _ in range(args.warmup):
+            p4.command_resident()
+        barrier()
+        n4 = min(args.steps, 50)
+        ev4 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n4)]
+        for i in range(n4):
+            if flush is not None:
+                flush.fill_(i & 1)
+            ev4[i][0].record(stream)
+            p4.command_resident()
+            ev4[i][1].record(stream)
+        barrier()
+        ms4 = torch.tensor([a.elapsed_time(b) for a, b in ev4], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
+        m4 = float(ms4.mean())
+        n1_default = {"name": "c4", "workload": conf4["workload"], "K_global": conf4["K"] * world, "ms_per_step": m4,
+                      "value": conf4["K"] * world * conf4["T"] / (m4 * 1e-3), "steps": n4, "exchange": ex4,
+                      "note": "the workload of the default N = 1 line (bench.py --gpus 1), sharded over these GPUs the same "
+                              "way and timed the same way (device events, max over ranks, L2 flushed)"}
+        p4.close()
+        barrier()
     clocks = sampler.summary(t_timed0, t_timed1)
     nf = 22 if env == "point_env" else 53
     nu = 2 if env == "point_env" else 9
@@ -472,6 +500,8 @@ def main():
                          "note": "issue/latency-bound, not HBM-bound: the outputs stay in the 126 MB L2 (DRAM traffic < "
                                  "algorithmic bytes); see DESIGN.md 5"},
         }
+        if n1_default is not None:
+            line["n1_default_workload_at_this_n"] = n1_default
         if n1_same is not None:
             line["single_gpu_same_workload"] = n1_same
             line["weak_scaling_efficiency_same_workload"] = (line["value"] / world) / n1_same["value"]

@@ -255,6 +255,17 @@ def build_panda_scene(actors=None):
             if a.name == "shelf_stand":
                 s.idx_shelf = n
             n += 1
+    # the ground plane of the reference (z = 0, friction 1, isaacgym_wrapper.py:462-469) as a thick slab: a cube that
+    # leaves the table lands on it instead of falling for ever
+    if n < A.MAX_STATIC:
+        g = A.Box()
+        _fill(g.pos, [0.0, 0.0, -0.5])
+        _fill(g.half, [10.0, 10.0, 0.5])
+        _fill(g.quat, [0.0, 0.0, 0.0, 1.0])
+        g.mu = 1.0
+        g.actor = -1
+        s.statics[n] = g
+        n += 1
     s.n_static = n
     for key, value in PANDA_SCENE_OVERRIDES.items():
         setattr(s, key, value)

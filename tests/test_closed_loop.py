@@ -183,6 +183,36 @@ def _check_grasp(fingers, f_table, cube):
     assert fingers[-1].min() > 0.024
 
 
+def _drop_cube(factory):
+    """cubeA placed beyond the table edge falls onto the ground plane of the reference (z = 0, isaacgym_wrapper.py:462-469)
+    and comes to rest there; cubeB stays asleep on the table."""
+    cfg = S.make_cfg("panda_env", "pick", None, 1, 16)
+    real = wrapper.IsaacGymWrapper(cfg.isaacgym, "panda_env", num_envs=1, device="cpu", backend_factory=factory)
+    ia, ib = real._get_actor_index_by_name("cubeA"), real._get_actor_index_by_name("cubeB")
+    real._root_state[0, ia, 0] = 1.0   # the table top ends at x = 0.6
+    real._root_state[0, ia, 7:] = 0
+    real.set_actor_root_state_tensor(real._root_state)
+    for _ in range(150):
+        real.step()
+    return real._root_state[0, ia].clone().numpy(), real._root_state[0, ib].clone().numpy()
+
+
+def _check_drop(a, b):
+    assert abs(a[2] - 0.025) < 2e-3, a[:3]           # the 5 cm cube rests on z = 0
+    assert np.abs(a[7:10]).max() < 2e-2, a[7:10]
+    assert abs(a[0] - 1.0) < 5e-3 and abs(a[1] + 0.2) < 5e-3, a[:3]
+    assert abs(b[2] - 1.05) < 2e-3, b[:3]
+
+
+def test_cube_lands_on_the_ground_cpu():
+    _check_drop(*_drop_cube(O.Oracle.for_sim))
+
+
+@pytest.mark.gpu
+def test_cube_lands_on_the_ground_gpu():
+    _check_drop(*_drop_cube(None))
+
+
 def test_grasp_holds_and_lifts_cpu(monkeypatch):
     _check_grasp(*_squeeze_and_lift(O.Oracle.for_sim, monkeypatch))
 
