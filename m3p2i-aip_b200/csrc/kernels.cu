@@ -141,6 +141,18 @@ static int rollout_block(int K) {
 // duration is set by the SM that received the most warps: pick the warps-per-CTA w in 2..7 that minimises
 // ceil(#CTAs / #SMs) * w, preferring large CTAs (their warps are re-aligned every sub-step and share
 // instruction-cache lines). K = 4096 with 8-lane teams: w = 7 -> 147 CTAs, one per SM.
+// Function attributes (dynamic shared memory above 48 KB) are per device: true the first time `what` is asked for on
+// the current device of this process (handles of one process may live on different GPUs).
+static bool first_use_on_device(int what) {
+  static unsigned char done[2][64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return true;
+  if (done[what][dev]) return false;
+  done[what][dev] = 1;
+  return true;
+}
+
 static int team_sms() {
   static int sms = 0;
   if (!sms) {
@@ -187,14 +199,12 @@ void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, co
     const size_t smem = (size_t)7 * (16 / c.lanes) * sizeof(float4) * tb +
                         (size_t)(tb / c.lanes) * 2 * kRecStride * sizeof(float4) +
                         (need_refs ? (size_t)(tb / c.lanes) * 2 * c.T * sizeof(float4) : 0);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (first_use_on_device(0)) {
       // CPL = 2, largest CTA, longest horizon: above the 48 KB default
       const int max_smem = 7 * 2 * (int)sizeof(float4) * kTeamBlockMax +
                            (kTeamBlockMax / 8) * 2 * (kRecStride + kMaxT) * (int)sizeof(float4);
       cudaFuncSetAttribute(k_rollout_team<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
       cudaFuncSetAttribute(k_rollout_team<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-      attr_set = true;
     }
     if (c.lanes == 16) k_rollout_team<1><<<tgrid, tb, smem, st>>>(c, *qp, b);
     else k_rollout_team<2><<<tgrid, tb, smem, st>>>(c, *qp, b);
@@ -364,9 +374,8 @@ __global__ void __launch_bounds__(kStatsBlock) k_stats(const UpdateCfg u, const 
 
 void launch_stats(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches) {
   // dynamic shared memory: the costs of the largest set, when they fit beside the reduction scratch
-  static bool attr_set = false;
   constexpr size_t kStageMax = 200 * 1024;
-  if (!attr_set) { cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageMax); attr_set = true; }
+  if (first_use_on_device(1)) cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageMax);
   UpdateCfg us = u;
   const size_t bytes = sizeof(float) * (size_t)u.Kg;
   us.stage_J = bytes <= kStageMax ? 1 : 0;

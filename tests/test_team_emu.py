@@ -21,7 +21,7 @@ from m3p2i_b200 import scene as S  # noqa: E402
 GRASP_Q = [-0.21448, 1.040633, -0.091726, -1.527796, 0.144743, 2.56178, 0.807333]
 
 
-def _case(task, fingers, K, T, shelf=False, mm=False, seed=0, sigma=1.0):
+def _case(task, fingers, K, T, shelf=False, mm=False, seed=0, sigma=1.0, lift=0.0):
     cfg = S.make_cfg("panda_env", task, None, K, T, multi_modal=mm, cube_on_shelf=shelf)
     c = S.build_config(cfg, noise_mode=A.NOISE_TABLE, seed=0)
     scene = S.build_panda_scene()
@@ -32,6 +32,8 @@ def _case(task, fingers, K, T, shelf=False, mm=False, seed=0, sigma=1.0):
     root[S.actor_index(actors, "cubeB"), 2] -= 0.0095
     if fingers is not None:
         dof[0::2] = GRASP_Q + [fingers, fingers]
+        dof[2] -= lift   # shoulder back: the gripper starts `lift` rad above the grasp pose
+
     cb = root[S.actor_index(actors, "cubeB")]
     goal = np.concatenate([cb[:3] + np.array([0, 0, 0.055], np.float32), cb[3:7]]).astype(np.float32) if task == "pick" \
         else np.zeros(7, np.float32)
@@ -70,6 +72,23 @@ def test_team_device_code_matches_oracle(task, fingers, K, T, lanes, shelf, mm, 
         assert np.allclose(st_t, st_o, rtol=1e-5, atol=1e-5)
         assert np.isclose(ch_t, ch_o, rtol=1e-3, atol=5e-3).all(), np.abs(ch_t - ch_o).max()
         assert np.abs(env_t[:, :44] - env_e[:, :44]).max() < 5e-3   # end states of the two kernel shapes
+
+
+@pytest.mark.parametrize("lift,lanes", [(0.15, 8), (0.15, 16), (0.3, 8)])
+def test_dormant_cubes_wake_up_like_the_oracle(lift, lanes):
+    """The gripper starts 0.2 - 0.3 m above cubeA -- inside / just outside the bounding sphere of hand + fingers the dormant
+    shortcut tests first -- and random actions take some rollouts down onto the cube and others away from it: the
+    sub-steps the kernels skip (both cubes asleep, no link box in reach) and the ones they do not must add up to the
+    oracle's trajectory, which has no such shortcut."""
+    c, scene, task, goal, grip, dof, root, a, st_o, ch_o = _case("pick", 0.04, 16, 12, sigma=1.5, lift=lift, seed=3)
+    st_e, ch_e, env_e, _ = E.rollout_actions(c, scene, task, goal, grip, dof, root, a, lanes)
+    assert np.allclose(st_e, st_o, rtol=1e-5, atol=1e-5)
+    assert np.isclose(ch_e, ch_o, rtol=1e-3, atol=5e-3).all(), np.abs(ch_e - ch_o).max()
+    st_t, ch_t, env_t = E.thread_rollout_actions(c, scene, task, goal, grip, dof, root, a)
+    assert np.isclose(ch_t, ch_o, rtol=1e-3, atol=5e-3).all(), np.abs(ch_t - ch_o).max()
+    moved = np.abs(env_e[:, 18:21] - env_e[0:1, 18:21]).max(axis=1) > 1e-4   # cubeA ended somewhere else than in rollout 0
+    if lift < 0.2:
+        assert moved.any() and not moved.all()   # some rollouts reached the cube, some never woke it
 
 
 def test_contact_rich_case_has_contacts():
