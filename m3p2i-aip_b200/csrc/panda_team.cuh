@@ -449,6 +449,32 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
   bool was_asleep = false;   // own cube slept through the previous sub-step of this rollout
   int k0_keep = 0;           // its support box then
   const int n_iter = T * ns;
+  // a sleeping cube's sub-step: the support carries its weight (reported forces)
+  auto book_weight = [&](int k0s) {
+    const float wgt = P.cube_mass[g] * P.gravity * h;
+    if (k0s == P.idx_table && P.report_cube) imp_table.z -= wgt;
+    if (k0s == P.idx_shelf && P.report_cube) imp_shelf.z -= wgt;
+    if (g == 1) imp_cubeb.z += wgt;
+  };
+  // end of a step: the contact forces the cost reads, from the impulse / penalty sums of its sub-steps
+  auto finish_forces = [&]() {
+    V3 pr = pen;
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) pr = pr + shfl3(pr, t.lane ^ o);
+    const V3 pen_o = shfl3(pr, t.other);
+    const V3 pen_table = g == 0 ? pr : pen_o, pen_shelf = g == 0 ? pen_o : pr;
+    const V3 it_o = shfl3(imp_table, t.other), is_o = shfl3(imp_shelf, t.other), ib_o = shfl3(imp_cubeb, t.other);
+    const V3 itab = g == 0 ? imp_table + it_o : it_o + imp_table;   // cubeA's share first, as in the serial order
+    const V3 ishf = g == 0 ? imp_shelf + is_o : is_o + imp_shelf;
+    const V3 icb = g == 1 ? imp_cubeb : ib_o;
+    const float inv_dt = 1.0f / c.dt, inv_ns = 1.0f / (float)ns;
+    e.f_table = inv_dt * itab + inv_ns * pen_table;
+    e.f_shelf = inv_dt * ishf + inv_ns * pen_shelf;
+    e.f_cubeb = inv_dt * icb;
+  };
+  // ---- far field (see the block in the loop): needs sub-steps that tile the run-ahead blocks
+  const bool far_cfg = (ns & (ns - 1)) == 0 && ns <= TM && !(use_refs && !producer && c.task != M3P2I_TASK_REACH);
+  int far_failed = -1;       // first iteration of the block in which the far-field attempt failed
 #pragma unroll 1
   for (int it = 0, step = 0, s = 0; it <= n_iter; ++it, s = (s + 1 == ns ? 0 : s + 1), step += (s == 0)) {
     const bool last = it == n_iter;
@@ -517,6 +543,137 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
         }
       }
       fk_from_sincos(P, ssn, scs, sqd, Hl);
+    }
+    // ---- far field: the rest of this run-ahead block in ONE lane-parallel pass. When both cubes of every sample of the
+    // warp slept through the previous sub-step, the only things that evolve are the arm (already advanced through the
+    // block above) and the two fingers (a cheap recurrence nobody else acts on). Lane l then evaluates iteration blk0 + l
+    // on its own -- link box centres from its own forward kinematics, the dormancy pre-tests of BOTH cubes, the
+    // bounding-sphere test of the gripper against table and shelf, and the cost of the step that ends there. If every
+    // iteration of the block passes every test, the serial path would have taken its dormant shortcut and skipped the
+    // link penalties in each of them: the block is committed (costs added in step order) and the loop jumps to the next
+    // block. Otherwise nothing is kept and the iterations run one by one as before (exact either way).
+    if (far_cfg && s == 0 && !last && far_failed != it - lb_ && __all_sync(kFull, was_asleep)) {
+      const int lend = min(TM, n_iter - (it - lb_));   // iterations [lb_, lend) of the block are left
+      // fingers through the block (every lane the same): drive, limits, position; lane l keeps the openings iteration l sees
+      float fq[2] = {e.q[7], e.q[8]}, fv[2] = {e.qd[7], e.qd[8]}, fu[2] = {uf[0], uf[1]};
+      float q7s = fq[0], q8s = fq[1];
+      {
+        int si = 0;
+#pragma unroll 1
+        for (int l = lb_; l < lend; ++l, si = (si + 1 == ns ? 0 : si + 1)) {
+          if (si == 0) { fu[0] = __shfl_sync(kFull, ul[7], t.team_base + l); fu[1] = __shfl_sync(kFull, ul[8], t.team_base + l); }
+          if (t.tl == l) { q7s = fq[0]; q8s = fq[1]; }
+#pragma unroll
+          for (int jf = 0; jf < 2; ++jf) {
+            const float qj = fq[jf], vj = fv[jf], uj = fu[jf];
+            const float m = P.finger_mass;
+            float vs = (m * vj + h * D * uj) / (m + h * D);
+            const float f = D * (uj - vs);
+            if (f > P.effort[7 + jf]) vs = vj + h * P.effort[7 + jf] / m;
+            else if (f < -P.effort[7 + jf]) vs = vj - h * P.effort[7 + jf] / m;
+            vs = clampf(vs, -P.qd_limit[7 + jf], P.qd_limit[7 + jf]);
+            if (qj <= P.q_lower[7 + jf] && vs < 0.0f) vs = 0.0f;
+            if (qj >= P.q_upper[7 + jf] && vs > 0.0f) vs = 0.0f;
+            vs = clampf(vs, -P.qd_limit[7 + jf], P.qd_limit[7 + jf]);
+            float qn = qj + h * vs;
+            if (qn < P.q_lower[7 + jf]) { qn = P.q_lower[7 + jf]; vs = 0.0f; }
+            if (qn > P.q_upper[7 + jf]) { qn = P.q_upper[7 + jf]; vs = 0.0f; }
+            fq[jf] = qn; fv[jf] = vs;
+          }
+        }
+      }
+      const bool act = t.tl >= lb_ && t.tl < lend;          // this lane holds an iteration of the rest of the block
+      const bool ends_step = act && (t.tl & (ns - 1)) == 0;  // ... the first sub-step of a step: the cost of the step before
+      const int step_l = step + ((t.tl - lb_) >> (31 - __clz(ns)));
+      V3 ll[3];
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        const float* cen = f < 2 ? P.finger_center : P.hand_center;
+        V3 l = mk(cen[0], cen[1], cen[2]);
+        if (f == 0) { l.y += q7s; l.z += kFingerZ; }
+        if (f == 1) { l.y = -l.y - q8s; l.z += kFingerZ; }
+        ll[f] = Hl.p + mul(Hl.R, l);
+      }
+      bool ok = true;
+      {
+        const V3 xo = shfl3(e.cu.p, t.other);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const V3 px = q == 0 ? e.cu.p : xo;
+          const float rad = q == 0 ? rad_own : rad_oth;
+          const V3 d2 = ll[2] - px;
+          const float rf = frad + rad + P.contact_margin, rh = hrad + rad + P.contact_margin;
+          const float rfar = rh + kGripReach, dd2 = dot(d2, d2);
+          bool dorm = dd2 > rh * rh;
+          if (dorm && !(dd2 > rfar * rfar)) {
+            const V3 d0 = ll[0] - px, d1 = ll[1] - px;
+            dorm = dot(d0, d0) > rf * rf && dot(d1, d1) > rf * rf;
+          }
+          ok = ok && dorm;
+        }
+        OBox3 gb;
+        gb.c = ll[2]; gb.R = Hl.R; gb.half = mk(hrad + kGripReach, 0.0f, 0.0f);
+        if (P.idx_table >= 0) ok = ok && !boxes_near(gb, obox_of(P.st[P.idx_table]), 0.0f);
+        if (P.idx_shelf >= 0) ok = ok && !boxes_near(gb, obox_of(P.st[P.idx_shelf]), 0.0f);
+      }
+      if (__all_sync(kFull, ok || !act)) {
+        // forces the previous step reported (read by the cost at lane lb_), then those of a step slept through
+        const V3 ft0 = e.f_table, fs0 = e.f_shelf, fb0 = e.f_cubeb;
+        imp_table = mk(0, 0, 0); imp_shelf = mk(0, 0, 0); imp_cubeb = mk(0, 0, 0); pen = mk(0, 0, 0);
+        for (int q = 0; q < ns; ++q) book_weight(k0_keep);
+        finish_forces();
+        const int src = t.team_base;  // a lane of group 0 holds cubeA
+        Cube a;
+        a.p = shfl3(e.cu.p, src);
+        a.qx = __shfl_sync(kFull, e.cu.qx, src); a.qy = __shfl_sync(kFull, e.cu.qy, src);
+        a.qz = __shfl_sync(kFull, e.cu.qz, src); a.qw = __shfl_sync(kFull, e.cu.qw, src);
+        a.v = mk(0, 0, 0); a.w = mk(0, 0, 0);
+        const bool costs = ends_step && step_l > 0;
+        const int ps = step_l - 1;
+        float cost_l = 0.0f;
+        if (producer) {
+          if (costs && (which == 0 || (which == 1 && c.multi_modal))) {
+            PandaRef* r = b.refs + ps;
+            if (which == 0) { r->cube0[0] = a.p.x; r->cube0[1] = a.p.y; r->cube0[2] = a.p.z; }
+            if (which == 1 || !c.multi_modal) r->sel_axis = sel_axis_of(a);
+          }
+        } else if (defer_reach) {
+          if (costs) {
+            const ReachParts rp = reach_parts(Hl, q7s, q8s, a, c, kg);
+            float4* slot = sreach + 2 * ps;
+            slot[0] = make_float4(rp.ee.x, rp.ee.y, rp.ee.z, rp.min_y);
+            slot[1] = make_float4(rp.dz.x, rp.dz.y, rp.dz.z, 0.0f);
+          }
+        } else {
+          if (costs) {
+            PandaRef ref;
+            ref.cube0[0] = a.p.x; ref.cube0[1] = a.p.y; ref.cube0[2] = a.p.z; ref.sel_axis = sel_axis_of(a);
+            const bool fst = t.tl == lb_;
+            const V3 ft = fst ? ft0 : e.f_table, fs = fst ? fs0 : e.f_shelf, fb = fst ? fb0 : e.f_cubeb;
+            const float fx = ft.x + 4.0f * fs.x + fb.x, fy = ft.y + 4.0f * fs.y + fb.y;
+            const float motion = (fabsf(fx) + fabsf(fy)) > 0.1f ? 1000.0f : 0.0f;
+            cost_l = panda_cost_from_hand(Hl, q7s, q8s, a, motion, c, kg, ref);
+            if (valid) b.cost_h[(size_t)ps * K + k] = cost_l;
+          }
+          int st = step;
+#pragma unroll 1
+          for (int l = lb_; l < lend; l += ns, ++st) {
+            const float cl = __shfl_sync(kFull, cost_l, t.team_base + l);
+            if (st > 0) { run += cl; J += gam * cl; gam *= c.gamma; }
+          }
+        }
+        e.q[7] = fq[0]; e.q[8] = fq[1]; e.qd[7] = fv[0]; e.qd[8] = fv[1];
+        uf[0] = fu[0]; uf[1] = fu[1];
+#pragma unroll
+        for (int sl = 0; sl < CPL; ++sl) lam_st[sl] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        prev_st = 0u; prev_lk = 0u; prev_cc = 0u;
+        // the barriers of the iterations that are skipped (every warp of the CTA passes the same number of them)
+        if (c.align) for (int q = lb_ + 1; q < lend; ++q) __syncthreads();
+        const int adv = lend - lb_;
+        it += adv - 1; step += adv / ns - 1; s = ns - 1;   // the loop header moves on to the first iteration after the block
+        continue;
+      }
+      far_failed = it - lb_;
     }
     // ---- hand pose of this iteration, from the lane that ran its forward kinematics
     Hand H;
@@ -621,10 +778,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       }
     }
     if (__all_sync(kFull, dormant)) {
-      const float wgt = P.cube_mass[g] * P.gravity * h;   // the support carries the weight
-      if (k0_keep == P.idx_table && P.report_cube) imp_table.z -= wgt;
-      if (k0_keep == P.idx_shelf && P.report_cube) imp_shelf.z -= wgt;
-      if (g == 1) imp_cubeb.z += wgt;
+      book_weight(k0_keep);
 #pragma unroll
       for (int sl = 0; sl < CPL; ++sl) lam_st[sl] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       prev_st = 0u; prev_lk = 0u; prev_cc = 0u;
@@ -701,10 +855,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     }
     if (asleep) {
       v = mk(0, 0, 0); w = mk(0, 0, 0);
-      const float wgt = P.cube_mass[g] * P.gravity * h;   // the support carries the weight
-      if (k0 == P.idx_table && P.report_cube) imp_table.z -= wgt;
-      if (k0 == P.idx_shelf && P.report_cube) imp_shelf.z -= wgt;
-      if (g == 1) imp_cubeb.z += wgt;
+      book_weight(k0);
 #pragma unroll
       for (int sl = 0; sl < CPL; ++sl) sh0[sl].hit = false;
     } else {
@@ -946,20 +1097,8 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       cu.qx = nx * inv; cu.qy = ny * inv; cu.qz = nz * inv; cu.qw = nw * inv;
     }
     if (s == ns - 1) {
-      // ---- end of the step: reported contact forces, per-step stores
-      V3 pr = pen;
-#pragma unroll
-      for (int o = 1; o < G; o <<= 1) pr = pr + shfl3(pr, t.lane ^ o);
-      const V3 pen_o = shfl3(pr, t.other);
-      const V3 pen_table = g == 0 ? pr : pen_o, pen_shelf = g == 0 ? pen_o : pr;
-      const V3 it_o = shfl3(imp_table, t.other), is_o = shfl3(imp_shelf, t.other), ib_o = shfl3(imp_cubeb, t.other);
-      const V3 itab = g == 0 ? imp_table + it_o : it_o + imp_table;   // cubeA's share first, as in the serial order
-      const V3 ishf = g == 0 ? imp_shelf + is_o : is_o + imp_shelf;
-      const V3 icb = g == 1 ? imp_cubeb : ib_o;
-      const float inv_dt = 1.0f / c.dt, inv_ns = 1.0f / (float)ns;
-      e.f_table = inv_dt * itab + inv_ns * pen_table;
-      e.f_shelf = inv_dt * ishf + inv_ns * pen_shelf;
-      e.f_cubeb = inv_dt * icb;
+      // ---- end of the step: reported contact forces
+      finish_forces();
     }
   }
   if (producer) {

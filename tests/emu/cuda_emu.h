@@ -113,6 +113,7 @@ inline unsigned reduce_max(unsigned v, int site) {
 
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline int __float_as_int(float a) { int r; memcpy(&r, &a, 4); return r; }
