@@ -109,6 +109,9 @@ struct M3P2IHandle_ {
   DevBuf<PandaRef> refs;
   DevBuf<unsigned> ref_flags;
   unsigned ref_epoch = 0;
+  DevBuf<int> near_list, near_count, far_info;   // far-field split (panda_far.cuh): rows left for the full rollout, two counters
+  DevBuf<float> far_dump;                        // joint states of those rows at their hand-over boundaries
+  unsigned far_epoch = 0;
   DevBuf<Stats> stats;
   DevBuf<M3P2ICommandInfo> info;
   bool have_noise = false, have_row0 = false, have_filt = false, have_evr = false;
@@ -272,6 +275,7 @@ RolloutBufs make_rbufs(const H* h) {
   b.actions = h->actions.p; b.states = h->states.p; b.cost_h = h->cost_h.p; b.J = h->J.p; b.cost_sum = h->cost_sum.p;
   b.refs = nullptr;
   b.ref_flags = h->ref_flags.p;
+  b.near_list = nullptr; b.near_count = nullptr; b.near_count_next = nullptr; b.far_info = nullptr; b.far_dump = nullptr;
   memset(&b.peer, 0, sizeof(b.peer));
   return b;
 }
@@ -385,6 +389,14 @@ int run_rollout(H* h, int* launches, const float* actions_in_dev, bool push_peer
     c.epoch = h->ref_epoch;
   }
   if (h->peer_on && push_peers) fill_peer(h, &b.peer, nullptr);
+  if (h->near_list.p) {
+    // counters alternate: this command's was cleared by the previous far-field launch (or is still zero)
+    b.near_list = h->near_list.p;
+    b.near_count = h->near_count.p + (h->far_epoch & 1u);
+    b.near_count_next = h->near_count.p + ((h->far_epoch + 1u) & 1u);
+    b.far_info = h->far_info.p; b.far_dump = h->far_dump.p;
+    if (far_rollout_applies(h->cfg.env_type, c, b, refs)) ++h->far_epoch;
+  }
   launch_rollout(h->cfg.env_type, c, &h->pp, &h->qp, b, refs, h->stream, launches);
   CK(cudaGetLastError());
   if (h->env_alloc) h->env_live = true;
@@ -587,6 +599,11 @@ int m3p2i_create(const M3P2IConfig* cfg, int device, m3p2i_handle* out) {
                                                       // [8] k_stats CTA counter, [9..11] beta iterations per set
   if (e == cudaSuccess) e = h->stats.alloc(1);
   if (e == cudaSuccess) e = h->info.alloc(1);
+  if (e == cudaSuccess && c.env_type == M3P2I_ENV_PANDA) e = h->near_list.alloc(K);
+  if (e == cudaSuccess && c.env_type == M3P2I_ENV_PANDA) e = h->near_count.alloc(2);
+  if (e == cudaSuccess && c.env_type == M3P2I_ENV_PANDA) e = h->far_info.alloc(8);
+  if (e == cudaSuccess && c.env_type == M3P2I_ENV_PANDA && c.substeps > 0)
+    e = h->far_dump.alloc(K * (size_t)far_boundaries((int)T, c.substeps) * 18);
   if (e == cudaSuccess) {
     Stats s;
     memset(&s, 0, sizeof(s));
@@ -638,6 +655,7 @@ void m3p2i_destroy(m3p2i_handle h) {
   h->cost_sum.release(); h->J_global.release(); h->weights.release(); h->partials.release(); h->filt.release();
   h->cost_total.release(); h->result.release(); h->links.release(); h->scratch.release(); h->states.release();
   h->refs.release(); h->ref_flags.release(); h->stats.release(); h->info.release();
+  h->near_list.release(); h->near_count.release(); h->far_info.release(); h->far_dump.release();
   if (h->pin) cudaFreeHost(h->pin);
   if (h->pin_base) cudaFreeHost(h->pin_base);
   if (h->mirror) cudaFreeHost(h->mirror);

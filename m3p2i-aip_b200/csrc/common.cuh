@@ -135,8 +135,22 @@ struct RolloutBufs {
   float* cost_sum;         // [K]  undiscounted sum
   PandaRef* refs;          // [T] rows 0 / Kg/2 of the batch, published step by step by the producer CTA
   unsigned* ref_flags;     // [2] progress counters of the two producers (cube position, cube axis)
+  // far-field split (panda_far.cuh): k_rollout_far finishes the samples that stay in the far field and lists the others;
+  // the rollout kernel launched after it processes exactly near_list[0 .. *near_count). nullptr: all K samples.
+  int* near_list;          // [K] rows of the samples that need the full rollout
+  int* near_count;         // their number (this command's counter)
+  int* near_count_next;    // the other parity's counter, cleared for the next command
+  int* far_info;           // [0], [1]: support box of cubeA / cubeB in the start state (the sleeping cubes' weight goes there)
+  float* far_dump;         // [K][far_boundaries][18] joint states of the listed samples at their hand-over boundaries
   PeerPush peer;
 };
+
+// Hand-over of a sample that leaves the far field at iteration i: the rollout kernel does not have to start it from
+// iteration 0 -- up to the last multiple of 8 iterations before i nothing but the nine joints moved. far_dump keeps, per
+// listed sample, (position, velocity) of the nine joints at the iterations 0, 8, 16, ... up to that boundary:
+// [K][far_boundaries][18]; the near list entry carries the boundary (bits 26..) next to the row (bits 0..25).
+__host__ __device__ inline int far_boundaries(int T, int ns) { return T * ns / 8 + 1; }
+constexpr int kFarRowBits = 26;
 
 // ------------------------------------------------------------------ small math
 // ------------------------------------------------------------------ programmatic dependent launch

@@ -63,12 +63,17 @@ k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename
   constexpr int NU = EnvOf<ENV>::NU;
   pdl_launch_dependents();   // k_stats may be set up while this grid runs; it waits for its completion (pdl_wait)
   const bool use_refs = ENV == M3P2I_ENV_PANDA && b.refs != nullptr;
+  // after k_rollout_far (panda_far.cuh): only the listed samples
+  const bool listed = ENV == M3P2I_ENV_PANDA && b.near_list != nullptr;
+  int count = c.K;
+  if (listed) count = __ldcg(b.near_count);
   if (use_refs && blockIdx.x == 0) {
-    if (ENV == M3P2I_ENV_PANDA) produce_refs(c, P, b, threadIdx.x);
+    if (ENV == M3P2I_ENV_PANDA && count > 0) produce_refs(c, P, b, threadIdx.x);
     return;
   }
-  const int k = (blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x + threadIdx.x;
-  if (k >= c.K) return;
+  const int kraw = (blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x + threadIdx.x;
+  if (kraw >= count) return;
+  const int k = listed ? (b.near_list[kraw] & ((1 << kFarRowBits) - 1)) : kraw;   // (always from iteration 0 here)
   const int K = c.K, kg = c.offset + k;
   Env e;
   if (c.env_live) e.load(b.env, K, k);
@@ -109,6 +114,7 @@ k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename
 }  // namespace m3
 
 #include "panda_team.cuh"
+#include "panda_far.cuh"
 #include "halton_spline.cuh"
 
 namespace m3 {
@@ -122,6 +128,66 @@ __global__ void __launch_bounds__(kTeamBlockMax, 1)
 k_rollout_team(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
   pdl_launch_dependents();   // k_stats may be set up while this grid runs; it waits for its completion (pdl_wait)
   team_kernel_body<CPL>(c, P, b);
+}
+
+// Far-field rollouts (panda_far.cuh): two samples per warp; with b.refs one more warp replays rows 0 and Kg/2 of the
+// batch. Samples that stay in the far field for the whole horizon are finished here; the others are listed for the
+// rollout kernel launched next (deterministic order inside a CTA, CTAs in the order of their atomic reservation).
+__global__ void __launch_bounds__(kFarBlockMax, 1)
+k_rollout_far(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
+  M3_DYNAMIC_SMEM(float4, far_smem);
+  __shared__ int s_prod_bad, s_near[kFarBlockMax / 32 + 1], s_base;
+  const bool use_refs = b.refs != nullptr;
+  const int warps = blockDim.x / 32, sample_warps = warps - (use_refs ? 1 : 0);
+  const int w = threadIdx.x / 32, lane = threadIdx.x & 31, team = lane / kFarLanes;
+  const bool prod = use_refs && w == sample_warps;
+  const int cta_first = blockIdx.x * sample_warps * kFarPerWarp;
+  const int kraw = cta_first + w * kFarPerWarp + team;
+  const bool valid = !prod && kraw < c.K;
+  int k = kraw < c.K ? kraw : c.K - 1, kg = c.offset + k;
+  if (prod) {
+    kg = (team == 1 && c.multi_modal) ? c.Kg / 2 : 0;
+    k = (kg >= c.offset && kg < c.offset + c.K) ? kg - c.offset : -1;
+  }
+  if (threadIdx.x == 0) {
+    s_prod_bad = 0;
+    if (blockIdx.x == 0) *b.near_count_next = 0;
+  }
+  __syncthreads();
+  float run = 0.0f, J = 0.0f;
+  int k0 = 0, bd = 0;   // support box of the lane's cube; hand-over boundary of a sample that leaves the far field
+  bool ok = far_base_asleep(c, P, k0);   // warp-uniform
+  if (blockIdx.x == 0 && w == 0 && (lane == 0 || lane == 8)) b.far_info[lane >> 3] = k0;
+  if (ok) ok = far_team_eval(c, P, b, reinterpret_cast<float*>(far_smem) + (size_t)w * kFarPerWarp * far_sample_floats(c.T, c.substeps),
+                             k, kg, valid, run, J, bd);
+  if (prod && !ok) s_prod_bad = 1;
+  __syncthreads();
+  if (s_prod_bad) { ok = false; bd = 0; }
+  // near list: rank inside the CTA from warp ballots, one reservation per CTA
+  const bool writer = valid && (lane & (kFarLanes - 1)) == 0;
+  const unsigned nb = __ballot_sync(0xffffffffu, writer && !ok);
+  if (lane == 0) s_near[w] = __popc(nb);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int i = 0; i < warps; ++i) { const int n = s_near[i]; s_near[i] = tot; tot += n; }
+    s_near[warps] = tot;
+    s_base = tot ? atomicAdd(b.near_count, tot) : 0;
+  }
+  __syncthreads();
+  if (writer && !ok) b.near_list[s_base + s_near[w] + __popc(nb & ((1u << lane) - 1u))] = k | (bd << kFarRowBits);
+  if (writer && ok) {
+    b.cost_sum[k] = run;
+    b.J[k] = J;
+    if (b.peer.n) push_J_store(b.peer, c.offset, k, J);
+  }
+  if (b.peer.n) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int here = min(sample_warps * kFarPerWarp, c.K - cta_first) - s_near[warps];
+      if (here > 0) push_J_commit(b.peer, c.K, (unsigned)here);
+    }
+  }
 }
 
 // Threads per CTA of the rollout kernel. The kernel is latency-bound (one serial chain per sample), so small CTAs
@@ -144,7 +210,7 @@ static int rollout_block(int K) {
 // Function attributes (dynamic shared memory above 48 KB) are per device: true the first time `what` is asked for on
 // the current device of this process (handles of one process may live on different GPUs).
 static bool first_use_on_device(int what) {
-  static unsigned char done[2][64] = {};
+  static unsigned char done[3][64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return true;
@@ -181,8 +247,47 @@ static int team_block(int K, int extra, int per_warp) {
   return 32 * best_w;
 }
 
+// shape of the far-field launch: sample warps per CTA (<= 14) that keeps the shared memory within `smem_cap` and spreads
+// the CTAs evenly over the SMs; 0 = the horizon does not fit
+static int far_sample_warps(int K, int T, int ns, int extra_warp, size_t smem_cap) {
+  const size_t per_warp = (size_t)kFarPerWarp * far_sample_floats(T, ns) * sizeof(float);
+  int wmax = kFarBlockMax / 32 - 1;
+  while (wmax > 0 && per_warp * (wmax + extra_warp) > smem_cap) --wmax;
+  if (wmax <= 0) return 0;
+  const int sms = team_sms();
+  int best_w = 1, best_load = 1 << 30;
+  for (int w = 1; w <= wmax; ++w) {
+    const int ctas = (K + kFarPerWarp * w - 1) / (kFarPerWarp * w);
+    const int load = ((ctas + sms - 1) / sms) * w;
+    if (load <= best_load) { best_load = load; best_w = w; }
+  }
+  return best_w;
+}
+
+bool far_rollout_applies(int env_type, const RolloutCfg& c, const RolloutBufs& b, bool need_refs) {
+  const char* env = getenv("M3P2I_FAR");   // M3P2I_FAR=0: every sample through the full rollout kernel (A/B tests)
+  const bool enabled = env ? atoi(env) != 0 : true;
+  if (!enabled || env_type != M3P2I_ENV_PANDA || c.env_live || c.store_env || !b.near_list) return false;
+  if (need_refs) return false;   // reach: rows 0 / Kg/2 of the batch usually head for the cube; they keep the one-kernel path
+  if (c.K >= (1 << kFarRowBits)) return false;
+  if (c.substeps <= 0 || (c.substeps & (c.substeps - 1))) return false;
+  return far_sample_warps(c.K, c.T, c.substeps, need_refs ? 1 : 0, 200 * 1024) > 0;
+}
+
 void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp,
-                    const RolloutBufs& b, bool need_refs, cudaStream_t st, int* launches) {
+                    const RolloutBufs& b_in, bool need_refs, cudaStream_t st, int* launches) {
+  RolloutBufs b = b_in;
+  if (far_rollout_applies(env_type, c, b, need_refs)) {
+    const int extra_warp = need_refs ? 1 : 0;
+    const int w = far_sample_warps(c.K, c.T, c.substeps, extra_warp, 200 * 1024);
+    const int fgrid = (c.K + kFarPerWarp * w - 1) / (kFarPerWarp * w);
+    const size_t fsmem = (size_t)(w + extra_warp) * kFarPerWarp * far_sample_floats(c.T, c.substeps) * sizeof(float);
+    if (first_use_on_device(2)) cudaFuncSetAttribute(k_rollout_far, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    k_rollout_far<<<fgrid, 32 * (w + extra_warp), fsmem, st>>>(c, *qp, b);
+    ++*launches;
+  } else {
+    b.near_list = nullptr; b.near_count = nullptr; b.near_count_next = nullptr; b.far_info = nullptr; b.far_dump = nullptr;
+  }
   const int block = rollout_block(c.K);
   const int extra = need_refs ? 1 : 0;   // CTA 0 = producer of the batch rows every reach cost reads
   const int grid = (c.K + block - 1) / block + extra;

@@ -47,6 +47,8 @@ struct UpdateBufs {
   PeerReduce peer;
 };
 
+// whether launch_rollout will run the far-field kernel (panda_far.cuh) in front of the rollout kernel for this command
+bool far_rollout_applies(int env_type, const RolloutCfg& c, const RolloutBufs& b, bool need_refs);
 void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, const PandaParams* qp,
                     const RolloutBufs& b, bool need_refs, cudaStream_t st, int* launches);
 void launch_stats(const UpdateCfg& u, const UpdateBufs& b, cudaStream_t st, int* launches);

@@ -388,7 +388,7 @@ DEV void fk_from_sincos(const PandaParams& P, const float* sn, const float* cs, 
 // team replaying a row of another shard), `kg` its global id. Producer teams publish refs instead of costs.
 template <int CPL>
 DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBufs& b, const TeamLane& t, int k, int kg,
-                      bool valid, bool producer, int which) {
+                      bool valid, bool producer, int which, int it0 = 0) {
   constexpr int NU = 9;
   constexpr int G = TeamShape<CPL>::kGroup, TM = TeamShape<CPL>::kTeam;
   const int K = c.K, T = c.T, ns = c.substeps;
@@ -406,6 +406,22 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
   if (c.env_live && k >= 0) e.load(b.env, K, k, g);
   else e.load(c.base_env, 1, 0, g);
   float run = 0.0f, J = 0.0f, gam = 1.0f;
+  if (it0 > 0) {
+    // hand-over from the far-field kernel (panda_far.cuh) at iteration it0 (warp-uniform; a multiple of the run-ahead
+    // block and of the sub-steps): until then only the joints moved -- their state at the boundary comes from the
+    // dump --, both cubes slept where they started, and the costs of the finished steps are in cost_h
+    const float* d = b.far_dump + ((size_t)k * far_boundaries(T, ns) + (it0 >> 3)) * 18;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { e.q[j] = d[2 * j]; e.qd[j] = d[2 * j + 1]; }
+    e.cu.v = mk(0, 0, 0); e.cu.w = mk(0, 0, 0);
+    const int done = it0 / ns;
+    for (int ts = 0; ts < done; ++ts) {
+      const float cost = b.cost_h[(size_t)ts * K + k];
+      run += cost;
+      J += gam * cost;
+      gam *= c.gamma;
+    }
+  }
   // group-partial impulse sums (identical in the lanes of a group), lane-partial penalty sums, per step
   V3 imp_table = mk(0, 0, 0), imp_shelf = mk(0, 0, 0), imp_cubeb = mk(0, 0, 0), pen = mk(0, 0, 0);
 
@@ -446,8 +462,8 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
   // box centre (the fingers reach 0.12 m from it: finger joint offset + finger box + stroke)
   const float frad = sqrtf(P.finger_half[0] * P.finger_half[0] + P.finger_half[1] * P.finger_half[1] + P.finger_half[2] * P.finger_half[2]);
   const float hrad = sqrtf(P.hand_half[0] * P.hand_half[0] + P.hand_half[1] * P.hand_half[1] + P.hand_half[2] * P.hand_half[2]);
-  bool was_asleep = false;   // own cube slept through the previous sub-step of this rollout
-  int k0_keep = 0;           // its support box then
+  bool was_asleep = it0 > 0; // own cube slept through the previous sub-step of this rollout
+  int k0_keep = it0 > 0 ? b.far_info[g] : 0;   // its support box then
   const int n_iter = T * ns;
   // a sleeping cube's sub-step: the support carries its weight (reported forces)
   auto book_weight = [&](int k0s) {
@@ -476,8 +492,9 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
   const bool far_cfg = (ns & (ns - 1)) == 0 && ns <= TM && !(use_refs && !producer && c.task != M3P2I_TASK_REACH);
   int far_failed = -1;       // first iteration of the block in which the far-field attempt failed
 #pragma unroll 1
-  for (int it = 0, step = 0, s = 0; it <= n_iter; ++it, s = (s + 1 == ns ? 0 : s + 1), step += (s == 0)) {
+  for (int it = it0, step = it0 / ns, s = 0; it <= n_iter; ++it, s = (s + 1 == ns ? 0 : s + 1), step += (s == 0)) {
     const bool last = it == n_iter;
+    const bool handed = it0 > 0 && it == it0;   // the cost of the step that ended at the hand-over is already counted
     // Re-align the warps of the CTA once per sub-step: they then walk the same stretch of this (large) loop body at
     // about the same time and share its instruction-cache lines instead of evicting each other's.
     if (c.align) __syncthreads();
@@ -628,7 +645,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
         a.qx = __shfl_sync(kFull, e.cu.qx, src); a.qy = __shfl_sync(kFull, e.cu.qy, src);
         a.qz = __shfl_sync(kFull, e.cu.qz, src); a.qw = __shfl_sync(kFull, e.cu.qw, src);
         a.v = mk(0, 0, 0); a.w = mk(0, 0, 0);
-        const bool costs = ends_step && step_l > 0;
+        const bool costs = ends_step && step_l > 0 && !(handed && t.tl == lb_);
         const int ps = step_l - 1;
         float cost_l = 0.0f;
         if (producer) {
@@ -659,7 +676,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
 #pragma unroll 1
           for (int l = lb_; l < lend; l += ns, ++st) {
             const float cl = __shfl_sync(kFull, cost_l, t.team_base + l);
-            if (st > 0) { run += cl; J += gam * cl; gam *= c.gamma; }
+            if (st > 0 && !(handed && l == lb_)) { run += cl; J += gam * cl; gam *= c.gamma; }
           }
         }
         e.q[7] = fq[0]; e.q[8] = fq[1]; e.qd[7] = fv[0]; e.qd[8] = fv[1];
@@ -702,7 +719,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       e.qd[8] = __shfl_sync(kFull, vs, t.team_base + 1);
     }
 
-    if (s == 0 && step > 0) {
+    if (s == 0 && step > 0 && !handed) {
       // ---- cost of the step that just ended (same joint positions as this FK; the drives only changed velocities)
       const int ps = step - 1;
       if (producer) {
@@ -1165,21 +1182,35 @@ DEV void team_kernel_body(const RolloutCfg& c, const PandaParams& P, const Rollo
   const bool use_refs = b.refs != nullptr;
   const bool producer = use_refs && blockIdx.x == 0;
   const int which = t.lane / TM;   // producer CTA: team 0 replays global row 0, team 1 global row Kg/2
+  // after k_rollout_far: only the listed samples (the far-field ones are finished); CTAs without work leave at once
+  int count = c.K;
+  if (b.near_list) count = __ldcg(b.near_count);
+  const int cta_first = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x) / TM;
+  if (count <= 0 || (!producer && cta_first >= count)) return;
   const int kraw = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x + threadIdx.x) / TM;
-  const bool valid = !producer && kraw < c.K;
-  int k = kraw < c.K ? kraw : c.K - 1;   // idle teams shadow the last sample so that every shuffle has 32 lanes
+  const bool valid = !producer && kraw < count;
+  int k = kraw < count ? kraw : count - 1;   // idle teams shadow the last sample so that every shuffle has 32 lanes
+  int it_start = 0;
+  if (b.near_list && !producer) {
+    // listed sample: row and hand-over boundary (panda_far.cuh). The warp starts at the earliest boundary of its
+    // samples, rounded down to a run-ahead block; a sample handed over later just repeats a few far-field iterations.
+    const int entry = b.near_list[k];
+    k = entry & ((1 << kFarRowBits) - 1);
+    const unsigned bd = __reduce_min_sync(kFull, (unsigned)(entry >> kFarRowBits));
+    it_start = ((int)bd * 8) & ~(TM - 1);
+  }
   int kg = c.offset + k;
   if (producer) {
     kg = (which == 1 && c.multi_modal) ? c.Kg / 2 : 0;
     k = (kg >= c.offset && kg < c.offset + c.K) ? kg - c.offset : -1;
   }
-  team_rollout<CPL>(c, P, b, t, k, kg, valid, producer, which);
+  team_rollout<CPL>(c, P, b, t, k, kg, valid, producer, which, it_start);
   if (b.peer.n && !producer) {
     // sharded over peer memory: the CTA's J values are in every mailbox; one thread orders them and counts them in
     __syncthreads();
     if (threadIdx.x == 0) {
-      const int first = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x) / TM;
-      const int cnt = min((int)blockDim.x / TM, c.K - first);
+      const int first = cta_first;
+      const int cnt = min((int)blockDim.x / TM, count - first);
       if (cnt > 0) push_J_commit(b.peer, c.K, (unsigned)cnt);
     }
   }

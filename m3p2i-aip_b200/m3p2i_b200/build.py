@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 OUT = os.path.join(HERE, "libm3p2i_b200.so")
 SOURCES = ["kernels.cu", "api.cu"]
-HEADERS = ["common.cuh", "point_env.cuh", "panda_env.cuh", "panda_team.cuh", "rollout_common.cuh", "kernels.cuh", "params_host.h", os.path.join("..", "..", "include", "m3p2i_b200.h")]
+HEADERS = ["common.cuh", "point_env.cuh", "panda_env.cuh", "panda_team.cuh", "panda_far.cuh", "rollout_common.cuh", "kernels.cuh", "params_host.h", os.path.join("..", "..", "include", "m3p2i_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-shared"]
 

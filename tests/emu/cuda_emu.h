@@ -107,6 +107,7 @@ inline unsigned reduce_max(unsigned v, int site) {
 #define __all_sync(mask, p) (emu::ballot((p), __LINE__) == 0xffffffffu)
 #define __syncwarp() ((void)emu::ballot(true, __LINE__))
 #define __reduce_max_sync(mask, v) emu::reduce_max((v), __LINE__)
+#define __reduce_min_sync(mask, v) (~emu::reduce_max(~(unsigned)(v), __LINE__))
 #define __syncthreads() do { fprintf(stderr, "emu: __syncthreads is not emulated (run with align = 0)\n"); abort(); } while (0)
 #define M3_PIN_VALUES9(a, b, c, d, e, f, g, h, i) do { } while (0)
 #define M3_DYNAMIC_SMEM(type, name) type* name = static_cast<type*>(emu::W->smem)

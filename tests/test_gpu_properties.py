@@ -231,3 +231,54 @@ def test_c5_shard_matches_oracle(offset):
         assert_close(J_n, J_o, 1e-3, 1e-3, f"c5 shard@{offset}[{tick}] discounted costs", 0.005)
     o.close()
     n.close()
+
+
+GRASP_Q = [-0.21448, 1.040633, -0.091726, -1.527796, 0.144743, 2.56178, 0.807333]
+
+
+@pytest.mark.parametrize("task,mm,shelf,lift,K", [
+    ("pick", False, False, None, 4096),    # C4 bench state: every rollout stays in the far field
+    ("reach", True, True, None, 4096),     # C5 shard: reach costs read the batch rows
+    ("pick", False, False, 0.5, 2048),     # gripper 0.3 m above cubeA: far and near samples mixed (16-lane teams)
+    ("pick", False, False, 0.5, 16384),    # the same through the thread-per-sample kernel
+    ("reach", False, False, 0.45, 4096),   # reach with near samples: the producer CTA publishes the rows
+    ("pick", False, False, 0.0, 1024),     # fingers around cubeA: nothing is far
+])
+def test_far_field_split_matches_full_rollout(monkeypatch, task, mm, shelf, lift, K):
+    """k_rollout_far + the rollout kernel over the near list (panda_far.cuh) against the rollout kernel over all K
+    samples (M3P2I_FAR=0): same per-sample costs, same state rows, same command, over several ticks."""
+    T = 32
+    cfg = S.make_cfg("panda_env", task, None, K, T, multi_modal=mm, cube_on_shelf=shelf)
+    actors = S.default_actors("panda_env")
+    dof, root = S.initial_dof_state(actors).copy(), S.initial_root_state(actors, shelf).copy()
+    if not shelf:
+        root[S.actor_index(actors, "cubeA"), 2] -= 0.0095
+    root[S.actor_index(actors, "cubeB"), 2] -= 0.0095
+    if lift is not None:
+        dof[0::2] = GRASP_Q + [0.04, 0.04]
+        dof[2] -= lift
+    cb = root[S.actor_index(actors, "cubeB")]
+    goal = np.concatenate([cb[:3] + np.array([0, 0, 0.055], np.float32), cb[3:7]]) if task == "pick" else np.zeros(7, np.float32)
+    res = {}
+    for far in ("1", "0"):
+        monkeypatch.setenv("M3P2I_FAR", far)
+        n = make_backend(native.NativePlanner, cfg, noise_mode=A.NOISE_PHILOX, seed=5)
+        n.set_state(dof, root)
+        n.set_objective(task, goal, {"pick": "close", "reach": "open"}[task])
+        out = []
+        for _ in range(3):
+            action, cost_total, info = n.command()
+            out.append((action, cost_total, n.read_buffer(A.BUF_COST_HORIZON), n.read_buffer(A.BUF_STATES),
+                        n.read_buffer(A.BUF_ACTIONS), info.launches))
+        res[far] = out
+        n.close()
+    for i, ((a1, c1, ch1, st1, ac1, l1), (a0, c0, ch0, st0, ac0, l0)) in enumerate(zip(res["1"], res["0"])):
+        assert l1 == l0 + (0 if task == "reach" else 1)   # one more launch: the far-field kernel (pick / place)
+        if i == 0:
+            assert np.array_equal(ac1, ac0) and np.array_equal(st1, st0)   # same planner state: same actions, same joints
+        else:
+            # later ticks start from planner states that may differ in the last bits (sums in a different kernel)
+            assert np.allclose(ac1, ac0, atol=1e-4) and np.allclose(st1, st0, atol=1e-4)
+        bad = ~np.isclose(ch1, ch0, rtol=1e-4, atol=1e-4)
+        assert bad.sum() <= 0.002 * bad.size, f"{bad.sum()} of {bad.size} step costs differ, max {np.abs(ch1 - ch0).max()}"
+        assert_close(a1, a0, 1e-4, 1e-4, "command")

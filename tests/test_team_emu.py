@@ -95,3 +95,54 @@ def test_contact_rich_case_has_contacts():
     """The grasp case above is not vacuous: the oracle's rollouts contain collision-cost steps and the cube moves."""
     *_, st_o, ch_o = _case("pick", 0.027, 16, 10)
     assert (ch_o > 900).any() and (ch_o < 900).any()
+
+
+@pytest.mark.parametrize("task,fingers,K,T,shelf,mm,lift,expect", [
+    ("pick", None, 12, 32, False, False, 0.0, "most"),     # the bench state: arm at its initial pose, cubes asleep
+    ("reach", None, 16, 32, True, True, 0.0, "most"),      # C5's state: multi-modal reach, cube on the shelf
+    ("place", None, 8, 12, False, False, 0.0, "most"),
+    ("pick", 0.04, 32, 24, False, False, 0.5, "some"),     # gripper 0.3 m above cubeA: some rollouts come down to it
+    ("pick", 0.027, 8, 10, False, False, 0.0, "none"),     # fingers closed on cubeA: nothing is far
+])
+def test_far_field_code_matches_team_and_oracle(task, fingers, K, T, shelf, mm, lift, expect):
+    """panda_far.cuh (the body of k_rollout_far): the samples it declares far carry exactly the costs, sums and state rows
+    the team kernel's device code and the oracle produce for them, and their cubes indeed never move; the others are left
+    to the full rollout."""
+    c, scene, task, goal, grip, dof, root, a, st_o, ch_o = _case(task, fingers, K, T, shelf, mm, lift=lift)
+    ok, pok, st, ch, cs, J = E.far_rollout_actions(c, scene, task, goal, grip, dof, root, a)
+    st_e, ch_e, env_e, _ = E.rollout_actions(c, scene, task, goal, grip, dof, root, a, 8)
+    assert {"most": ok.sum() >= K - 2, "some": 0 < ok.sum() < K, "none": ok.sum() == 0}[expect], ok.sum()
+    assert np.array_equal(st, st_e)                      # state rows: the same joint recurrences
+    assert np.array_equal(ch[ok], ch_e[ok])              # costs: the same functions on the same poses
+    assert np.isclose(ch[ok], ch_o[ok], rtol=1e-6, atol=2e-6).all()
+    if ok.any():
+        actors = S.default_actors("panda_env")
+        ra, rb = (np.asarray(root).reshape(-1, 13)[S.actor_index(actors, n)] for n in ("cubeA", "cubeB"))
+        start = np.concatenate([ra[:7], np.zeros(6, np.float32), rb[:7], np.zeros(6, np.float32)])
+        assert np.abs(env_e[ok][:, 18:44] - start).max() < 1e-6   # far samples: both cubes asleep where they started
+        g = np.float32(c.gamma) ** np.arange(T, dtype=np.float32)
+        assert np.allclose(cs[ok], ch[ok].sum(1), rtol=1e-5) and np.allclose(J[ok], (ch[ok] * g).sum(1), rtol=1e-5)
+    if task == "reach":
+        assert pok.all()   # rows 0 and K/2 stay far: the batch rows are the start pose
+
+
+@pytest.mark.parametrize("task,fingers,K,T,lift,sigma,seed", [
+    ("pick", None, 12, 32, 0.0, 1.0, 0),      # bench state: one rollout wanders off towards the table late in the horizon
+    ("pick", 0.04, 32, 24, 0.5, 1.0, 0),      # hand-overs at boundaries 0, 1, 2 and 4
+    ("pick", 0.04, 32, 32, 0.6, 1.0, 1),
+    ("place", 0.04, 16, 24, 0.5, 1.0, 0),
+    ("pick", 0.04, 16, 12, 0.15, 1.5, 3),     # the gripper starts inside its bounding sphere: everything from iteration 0
+])
+@pytest.mark.parametrize("lanes", [8, 16])
+def test_far_split_with_hand_over_matches_oracle(task, fingers, K, T, lift, sigma, seed, lanes):
+    """What a pick / place command launches: the far-field code over all samples, then the team kernel over the near list,
+    every listed sample starting at its warp's hand-over boundary (joints from the dump, finished costs from cost_h).
+    All K samples must carry the oracle's costs, sums and state rows."""
+    c, scene, task, goal, grip, dof, root, a, st_o, ch_o = _case(task, fingers, K, T, lift=lift, sigma=sigma, seed=seed)
+    st, ch, cs, J, far, bd = E.split_rollout_actions(c, scene, task, goal, grip, dof, root, a, lanes)
+    assert np.allclose(st, st_o, rtol=1e-5, atol=1e-5)
+    assert np.isclose(ch, ch_o, rtol=1e-3, atol=5e-3).all(), np.abs(ch - ch_o).max()
+    g = np.float32(c.gamma) ** np.arange(T, dtype=np.float32)
+    assert np.allclose(cs, ch.sum(1), rtol=1e-5, atol=1e-4) and np.allclose(J, (ch * g).sum(1), rtol=1e-5, atol=1e-4)
+    if lift in (0.5, 0.6):
+        assert far.any() and (~far).any() and (bd[~far] > 0).any()   # far samples, near samples and real hand-overs
