@@ -68,7 +68,8 @@ k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename
   int count = c.K;
   if (listed) count = __ldcg(b.near_count);
   if (use_refs && blockIdx.x == 0) {
-    if (ENV == M3P2I_ENV_PANDA && count > 0) produce_refs(c, P, b, threadIdx.x);
+    // (rows that stayed in the far field were published by k_rollout_far)
+    if (ENV == M3P2I_ENV_PANDA && count > 0 && !(listed && __ldcg(b.far_info + 2))) produce_refs(c, P, b, threadIdx.x);
     return;
   }
   const int kraw = (blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x + threadIdx.x;
@@ -163,6 +164,26 @@ k_rollout_far(const __grid_constant__ RolloutCfg c, const __grid_constant__ Pand
   if (prod && !ok) s_prod_bad = 1;
   __syncthreads();
   if (s_prod_bad) { ok = false; bd = 0; }
+  if (use_refs && blockIdx.x == 0) {
+    // rows 0 / Kg/2 of the batch stayed in the far field: their cubeA is the start state's at every step. Publish them
+    // for the samples of the near list (the rollout kernel's producer then has nothing to replay: far_info[2]).
+    if (threadIdx.x == 0) b.far_info[2] = s_prod_bad ? 0 : 1;
+    if (!s_prod_bad) {
+      TeamEnv e0;
+      e0.load(c.base_env, 1, 0, 0);
+      const int axis = sel_axis_of(e0.cu);
+      for (int t = threadIdx.x; t < c.T; t += blockDim.x) {
+        PandaRef* r = b.refs + t;
+        r->cube0[0] = e0.cu.p.x; r->cube0[1] = e0.cu.p.y; r->cube0[2] = e0.cu.p.z; r->sel_axis = axis;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        *(volatile unsigned*)(b.ref_flags + 0) = c.epoch + (unsigned)c.T;
+        *(volatile unsigned*)(b.ref_flags + 1) = c.epoch + (unsigned)c.T;
+      }
+    }
+  }
   // near list: rank inside the CTA from warp ballots, one reservation per CTA
   const bool writer = valid && (lane & (kFarLanes - 1)) == 0;
   const unsigned nb = __ballot_sync(0xffffffffu, writer && !ok);
@@ -268,7 +289,6 @@ bool far_rollout_applies(int env_type, const RolloutCfg& c, const RolloutBufs& b
   const char* env = getenv("M3P2I_FAR");   // M3P2I_FAR=0: every sample through the full rollout kernel (A/B tests)
   const bool enabled = env ? atoi(env) != 0 : true;
   if (!enabled || env_type != M3P2I_ENV_PANDA || c.env_live || c.store_env || !b.near_list) return false;
-  if (need_refs) return false;   // reach: rows 0 / Kg/2 of the batch usually head for the cube; they keep the one-kernel path
   if (c.K >= (1 << kFarRowBits)) return false;
   if (c.substeps <= 0 || (c.substeps & (c.substeps - 1))) return false;
   return far_sample_warps(c.K, c.T, c.substeps, need_refs ? 1 : 0, 200 * 1024) > 0;

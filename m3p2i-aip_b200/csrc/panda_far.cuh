@@ -94,6 +94,18 @@ DEV bool far_team_eval(const RolloutCfg& c, const PandaParams& P, const RolloutB
   float* const sc = sf + 2 * (n_iter + 1);                            // [T]
   float* const sbv = sc + T;                                          // [n_iter / 8 + 1][9] velocities at the boundaries
 
+  // pass 0: the tests of iteration 0 alone (the start state's joint positions, the same for every sample): when the gripper
+  // starts next to a cube or the table, nothing of this launch is far and the three phases are not worth running
+  // pass 1: the three phases
+  bool ok = true;
+  int first_bad = n_iter;   // first iteration of this lane that fails a test
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+  if (pass == 0) {
+    if (tl < 7) sq[tl] = c.base_env[2 * tl];
+    if (tl == 7 || tl == 8) sf[tl - 7] = c.base_env[2 * tl];
+    __syncwarp();
+  } else {
   // ---- 1. perturbed actions of the whole horizon
   for (int t = tl; t < T; t += TM) {
     float u[NU];
@@ -145,6 +157,7 @@ DEV bool far_team_eval(const RolloutCfg& c, const PandaParams& P, const RolloutB
     if ((n_iter & 7) == 0 && mine) sbv[(n_iter >> 3) * 9 + jo] = vo;
   }
   __syncwarp();
+  }   // pass 1
 
   // ---- 3. geometry tests and costs, lane l: iterations l, l + 16, ...
   TeamEnv e;   // cubeA of the start state (asleep: its pose is the pose of every step)
@@ -166,10 +179,8 @@ DEV bool far_team_eval(const RolloutCfg& c, const PandaParams& P, const RolloutB
   for (int g = 0; g < 2; ++g)
     rad_c[g] = sqrtf(P.cube_half[g][0] * P.cube_half[g][0] + P.cube_half[g][1] * P.cube_half[g][1] + P.cube_half[g][2] * P.cube_half[g][2]);
   const int ls = 31 - __clz(ns);   // ns is a power of two (checked by the launcher)
-  bool ok = true;
-  int first_bad = n_iter;   // first iteration of this lane that fails a test
 #pragma unroll 1
-  for (int i = tl; i <= n_iter; i += TM) {
+  for (int i = pass == 0 ? 0 : tl; i <= (pass == 0 ? 0 : n_iter); i += TM) {
     float sn[7], cs[7], qd0[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) { sincosf(sq[i * 8 + j], &sn[j], &cs[j]); qd0[j] = 0.0f; }
@@ -186,23 +197,59 @@ DEV bool far_team_eval(const RolloutCfg& c, const PandaParams& P, const RolloutB
         if (f == 1) { l.y = -l.y - q8; l.z += kFingerZ; }
         ll[f] = H.p + mul(H.R, l);
       }
+      // the cheap tests of the dormant shortcut first (bounding spheres); where one fails the exact tests of the full
+      // path decide: a link box whose sphere does not reach into the cube's box leaves the cube asleep (lnear == 0), and a
+      // link box without a corner inside table / shelf adds nothing to the penalty -- the rollout is still contact-free
+      bool dorm[2], sph[2];
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         const V3 px = g == 0 ? a.p : xb;
         const V3 d2 = ll[2] - px;
         const float rf = frad + rad_c[g] + P.contact_margin, rh = hrad + rad_c[g] + P.contact_margin;
         const float rfar = rh + kGripReach, dd2 = dot(d2, d2);
-        bool dorm = dd2 > rh * rh;
-        if (dorm && !(dd2 > rfar * rfar)) {
+        dorm[g] = dd2 > rh * rh;
+        if (dorm[g] && !(dd2 > rfar * rfar)) {
           const V3 d0 = ll[0] - px, d1 = ll[1] - px;
-          dorm = dot(d0, d0) > rf * rf && dot(d1, d1) > rf * rf;
+          dorm[g] = dot(d0, d0) > rf * rf && dot(d1, d1) > rf * rf;
         }
-        ok = ok && dorm;
       }
       OBox3 gb;
       gb.c = ll[2]; gb.R = H.R; gb.half = mk(hrad + kGripReach, 0.0f, 0.0f);
-      if (P.idx_table >= 0) ok = ok && !boxes_near(gb, obox_of(P.st[P.idx_table]), 0.0f);
-      if (P.idx_shelf >= 0) ok = ok && !boxes_near(gb, obox_of(P.st[P.idx_shelf]), 0.0f);
+      sph[0] = P.idx_table >= 0 && boxes_near(gb, obox_of(P.st[max(P.idx_table, 0)]), 0.0f);
+      sph[1] = P.idx_shelf >= 0 && boxes_near(gb, obox_of(P.st[max(P.idx_shelf, 0)]), 0.0f);
+      if (!(dorm[0] && dorm[1]) || sph[0] || sph[1]) {
+        bool touch = false;
+#pragma unroll 1
+        for (int f = 0; f < 3; ++f) {
+          OBox3 lb;
+          lb.c = f == 0 ? ll[0] : (f == 1 ? ll[1] : ll[2]); lb.R = H.R;
+          lb.half = f < 2 ? mk(P.finger_half[0], P.finger_half[1], P.finger_half[2]) : mk(P.hand_half[0], P.hand_half[1], P.hand_half[2]);
+#pragma unroll 1
+          for (int g = 0; g < 2; ++g) {
+            if (dorm[g]) continue;
+            TeamEnv ec;
+            ec.load(c.base_env, 1, 0, g);
+            OBox3 cb;
+            cb.c = ec.cu.p; cb.R = quat_to_R(ec.cu.qx, ec.cu.qy, ec.cu.qz, ec.cu.qw);
+            cb.half = mk(P.cube_half[g][0], P.cube_half[g][1], P.cube_half[g][2]);
+            const V3 dl = lb.c - cb.c;
+            const float rr = (f < 2 ? frad : hrad) + rad_c[g] + P.contact_margin;
+            if (dot(dl, dl) > rr * rr) continue;
+            if (boxes_near(lb, cb, P.contact_margin)) touch = true;
+          }
+#pragma unroll 1
+          for (int q = 0; q < 2; ++q) {
+            if (!sph[q]) continue;
+            const OBox3 sb = obox_of(P.st[q == 0 ? P.idx_table : P.idx_shelf]);
+            if (!boxes_near(lb, sb, 0.0f)) continue;
+            for (int cn = 0; cn < 8; ++cn) {
+              V3 n; float depth;
+              if (point_in_box(box_corner(lb, cn), sb, 0.0f, n, depth)) touch = true;
+            }
+          }
+        }
+        ok = ok && !touch;
+      }
       if (!ok) first_bad = min(first_bad, i);
     }
     if ((i & (ns - 1)) == 0 && i > 0) {
@@ -214,6 +261,11 @@ DEV bool far_team_eval(const RolloutCfg& c, const PandaParams& P, const RolloutB
       sc[(i >> ls) - 1] = cost;
     }
   }
+  if (pass == 0 && !__all_sync(kFull, ok)) {
+    run_out = 0.0f; J_out = 0.0f; boundary_out = 0;
+    return false;
+  }
+  }   // passes
   __syncwarp();   // the costs in sc are read by every lane of the team below
   const unsigned okb = __ballot_sync(kFull, ok);
   const bool team_ok = ((okb >> team_base) & 0xffffu) == 0xffffu;

@@ -1131,10 +1131,11 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     // steps l, l + TM, ...: cost ingredients from shared memory, the row of the batch from L2) and add up their parts.
     if (t.tl == 0) (void)ref_wait(b, T - 1, c.epoch, c.multi_modal != 0);
     __syncwarp();
-    float g_l = 1.0f, g_stride = 1.0f, run_l = 0.0f, J_l = 0.0f;
+    // (after a hand-over the steps before it0 are finished: their costs were added above, gam = gamma ^ (it0 / ns))
+    float g_l = gam, g_stride = 1.0f, run_l = 0.0f, J_l = 0.0f;
     for (int q = 0; q < TM; ++q) { if (q < t.tl) g_l *= c.gamma; g_stride *= c.gamma; }
 #pragma unroll 2
-    for (int ps = t.tl; ps < T; ps += TM) {
+    for (int ps = it0 / ns + t.tl; ps < T; ps += TM) {
       PandaRef ref;
       ref.cube0[0] = __ldcg(&b.refs[ps].cube0[0]); ref.cube0[1] = __ldcg(&b.refs[ps].cube0[1]);
       ref.cube0[2] = __ldcg(&b.refs[ps].cube0[2]); ref.sel_axis = __ldcg(&b.refs[ps].sel_axis);
@@ -1187,6 +1188,7 @@ DEV void team_kernel_body(const RolloutCfg& c, const PandaParams& P, const Rollo
   if (b.near_list) count = __ldcg(b.near_count);
   const int cta_first = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x) / TM;
   if (count <= 0 || (!producer && cta_first >= count)) return;
+  if (producer && b.near_list && __ldcg(b.far_info + 2)) return;   // k_rollout_far published the rows (they stayed far)
   const int kraw = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x + threadIdx.x) / TM;
   const bool valid = !producer && kraw < count;
   int k = kraw < count ? kraw : count - 1;   // idle teams shadow the last sample so that every shuffle has 32 lanes

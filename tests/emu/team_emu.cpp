@@ -245,7 +245,7 @@ int emu_split_rollout_actions(const M3P2IConfig* cfg, const M3P2IPandaScene* sce
                               const float* dof, const float* root, const float* actions, int lanes, int block_threads,
                               float* out_states, float* out_cost_h, float* out_cost_sum, float* out_J, int* out_far,
                               int* out_boundary) {
-  if (!cfg || !scene || !actions || (lanes != 8 && lanes != 16) || block_threads % 32 || task == M3P2I_TASK_REACH) return -1;
+  if (!cfg || !scene || !actions || (lanes != 8 && lanes != 16) || block_threads % 32) return -1;
   const int K = cfg->num_samples, T = cfg->horizon, NU = 9;
   PandaParams P;
   memset(&P, 0, sizeof(P));
@@ -281,24 +281,47 @@ int emu_split_rollout_actions(const M3P2IConfig* cfg, const M3P2IPandaScene* sce
   b.seq = seq.data(); b.actions_in = act_in.data(); memcpy(c.base_env, base.data(), sizeof(c.base_env));
   b.actions = act.data(); b.states = states.data(); b.cost_h = cost_h.data(); b.J = J.data(); b.cost_sum = cost_sum.data();
   b.far_info = info; b.far_dump = dump.data();
+  const bool refs = task == M3P2I_TASK_REACH;
+  std::vector<PandaRef> ref_buf(T);
+  unsigned flags[16] = {0};
+  c.epoch = 64;
+  b.refs = refs ? ref_buf.data() : nullptr; b.ref_flags = flags;
   emu::Warp* w = new emu::Warp();
   for (int l = 0; l < 32; ++l) w->lane[l].stack = static_cast<char*>(malloc(kStack));
   // 1. far-field code, warp by warp (k_rollout_far without its CTA-level bookkeeping)
   g_launch = {&c, &P, &b, 0};
   std::vector<float> fsm((size_t)kFarPerWarp * far_sample_floats(T, c.substeps));
+  bool prod_bad = false;
+  if (refs) {
+    // the warp of the batch rows first; rows that stay far are published as the start state's cube pose
+    int pok[2] = {0, 0};
+    g_far = {0, true, fsm.data(), pok, nullptr, nullptr, nullptr};
+    run_warp(*w, 0, 32, 0, nullptr);
+    prod_bad = !(pok[0] && pok[1]);
+    info[2] = prod_bad ? 0 : 1;
+    if (!prod_bad) {
+      Cube a;
+      a.p = mk(base[18], base[19], base[20]); a.qx = base[21]; a.qy = base[22]; a.qz = base[23]; a.qw = base[24];
+      a.v = mk(0, 0, 0); a.w = mk(0, 0, 0);
+      for (int t = 0; t < T; ++t) { ref_buf[t].cube0[0] = a.p.x; ref_buf[t].cube0[1] = a.p.y; ref_buf[t].cube0[2] = a.p.z; ref_buf[t].sel_axis = sel_axis_of(a); }
+      flags[0] = flags[1] = c.epoch + (unsigned)T;
+    }
+  }
   for (int k0 = 0; k0 < K; k0 += kFarPerWarp) {
     g_far = {k0, false, fsm.data(), ok.data(), cost_sum.data(), J.data(), bd.data()};
     run_warp(*w, 0, 32, 0, nullptr);
   }
-  for (int k = 0; k < K; ++k)
+  for (int k = 0; k < K; ++k) {
+    if (prod_bad) { ok[k] = 0; bd[k] = 0; }
     if (!ok[k]) list[count++] = k | (bd[k] << kFarRowBits);
+  }
   // 2. the team kernel over the near list
   b.near_list = list.data(); b.near_count = &count; b.near_count_next = &count_next;
   const int cpl = 16 / lanes, teams_per_block = block_threads / lanes;
-  const int grid = (K + teams_per_block - 1) / teams_per_block;
+  const int grid = (K + teams_per_block - 1) / teams_per_block + (refs ? 1 : 0);
   g_launch = {&c, &P, &b, cpl};
   std::vector<float4> smem((size_t)7 * cpl * block_threads + (size_t)(block_threads / lanes) * 2 * (kRecStride + T));
-  for (int blk = 0; blk < grid; ++blk)
+  for (int blk = 0; blk < grid; ++blk)   // CTA 0 (the producer of the reach rows) first, as on the GPU
     for (int wi = 0; wi < block_threads / 32; ++wi) run_warp(*w, blk, block_threads, wi, smem.data());
   for (int l = 0; l < 32; ++l) free(w->lane[l].stack);
   delete w;

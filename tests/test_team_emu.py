@@ -112,7 +112,8 @@ def test_far_field_code_matches_team_and_oracle(task, fingers, K, T, shelf, mm, 
     ok, pok, st, ch, cs, J = E.far_rollout_actions(c, scene, task, goal, grip, dof, root, a)
     st_e, ch_e, env_e, _ = E.rollout_actions(c, scene, task, goal, grip, dof, root, a, 8)
     assert {"most": ok.sum() >= K - 2, "some": 0 < ok.sum() < K, "none": ok.sum() == 0}[expect], ok.sum()
-    assert np.array_equal(st, st_e)                      # state rows: the same joint recurrences
+    if expect != "none":                                  # (gripper next to a cube at the start: early-out, nothing stored)
+        assert np.array_equal(st, st_e)                  # state rows: the same joint recurrences
     assert np.array_equal(ch[ok], ch_e[ok])              # costs: the same functions on the same poses
     assert np.isclose(ch[ok], ch_o[ok], rtol=1e-6, atol=2e-6).all()
     if ok.any():
@@ -131,18 +132,35 @@ def test_far_field_code_matches_team_and_oracle(task, fingers, K, T, shelf, mm, 
     ("pick", 0.04, 32, 24, 0.5, 1.0, 0),      # hand-overs at boundaries 0, 1, 2 and 4
     ("pick", 0.04, 32, 32, 0.6, 1.0, 1),
     ("place", 0.04, 16, 24, 0.5, 1.0, 0),
-    ("pick", 0.04, 16, 12, 0.15, 1.5, 3),     # the gripper starts inside its bounding sphere: everything from iteration 0
+    ("pick", 0.04, 16, 12, 0.15, 1.5, 3),     # the gripper starts inside its bounding sphere (exact tests decide), early hand-overs
+    ("pick", 0.04, 24, 32, 0.45, 1.5, 2),
 ])
 @pytest.mark.parametrize("lanes", [8, 16])
 def test_far_split_with_hand_over_matches_oracle(task, fingers, K, T, lift, sigma, seed, lanes):
+    _split_case(task, fingers, K, T, False, False, lift, sigma, seed, lanes)
+
+
+@pytest.mark.parametrize("fingers,K,T,shelf,mm,lift,sigma,seed", [
+    (None, 16, 32, True, True, 0.0, 1.0, 0),       # C5's state: rows 0 and K/2 stay far, published by the far-field code
+    (0.04, 32, 24, False, False, 0.5, 1.0, 0),     # near samples wait for nothing: the rows are already there
+    (0.04, 32, 24, False, True, 0.5, 1.0, 1),
+    (0.04, 32, 32, False, False, 0.45, 1.5, 2),    # hand-overs at 3, 5, 6, 7 with deferred reach costs
+    (0.04, 12, 8, False, False, 0.0, 0.5, 0),      # gripper astride cubeA: early-out, the producer CTA replays the rows
+])
+@pytest.mark.parametrize("lanes", [8, 16])
+def test_far_split_reach_matches_oracle(fingers, K, T, shelf, mm, lift, sigma, seed, lanes):
+    _split_case("reach", fingers, K, T, shelf, mm, lift, sigma, seed, lanes)
+
+
+def _split_case(task, fingers, K, T, shelf, mm, lift, sigma, seed, lanes):
     """What a pick / place command launches: the far-field code over all samples, then the team kernel over the near list,
     every listed sample starting at its warp's hand-over boundary (joints from the dump, finished costs from cost_h).
     All K samples must carry the oracle's costs, sums and state rows."""
-    c, scene, task, goal, grip, dof, root, a, st_o, ch_o = _case(task, fingers, K, T, lift=lift, sigma=sigma, seed=seed)
+    c, scene, task, goal, grip, dof, root, a, st_o, ch_o = _case(task, fingers, K, T, shelf, mm, lift=lift, sigma=sigma, seed=seed)
     st, ch, cs, J, far, bd = E.split_rollout_actions(c, scene, task, goal, grip, dof, root, a, lanes)
     assert np.allclose(st, st_o, rtol=1e-5, atol=1e-5)
     assert np.isclose(ch, ch_o, rtol=1e-3, atol=5e-3).all(), np.abs(ch - ch_o).max()
     g = np.float32(c.gamma) ** np.arange(T, dtype=np.float32)
     assert np.allclose(cs, ch.sum(1), rtol=1e-5, atol=1e-4) and np.allclose(J, (ch * g).sum(1), rtol=1e-5, atol=1e-4)
-    if lift in (0.5, 0.6):
+    if task == "pick" and lift in (0.5, 0.6):
         assert far.any() and (~far).any() and (bd[~far] > 0).any()   # far samples, near samples and real hand-overs
