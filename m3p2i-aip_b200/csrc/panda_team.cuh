@@ -290,67 +290,91 @@ DEV LinkHit link_hit(bool hit, V3 n, float depth, V3 pt, V3 hv, V3 hw, V3 hp, V3
 // kernel do the same). kRecStride = float4 per list; the odd 4-word pad puts the lists of a warp in different banks.
 constexpr int kRecStride = 4 * kLinkCap + 1;
 
-// One visit of the serial Gauss-Seidel chain: the equations of solve_contact3_acc for a kinematic link (one sliding DoF
-// for a finger) against a free cube, geometry terms from the record, accumulator of the slot read and written in
-// shared memory (one lane per cube walks the chain). `first`: the
-// slot's first visit of the sub-step applies its warm start (prepared by warm_prepare at detection). The link of the
-// record (bits 24.. of its last word) selects the sliding DoF: slide[0] / slide[1] for the fingers, none for the hand.
-// Returns the impulse on the link when WANT_SUM (cubeB's contacts are reported), else zero.
+// The serial Gauss-Seidel chain over the record list of one cube, walked by the cube's first lane (`n_own` = length of
+// its list; 0 in every other lane, which only takes part in the votes). A visit is the equations of solve_contact3_acc
+// for a kinematic link (one sliding DoF for a finger) against a free cube, geometry terms from the record, accumulator
+// of the slot read and written in shared memory. `first`: the slot's first visit of the sub-step applies its warm start
+// (prepared by warm_prepare at detection). The link of the record (bits 24.. of its last word) selects the sliding DoF:
+// slide[0] / slide[1] for the fingers, none for the hand.
+// Most contacts of a grasp are OPEN (speculative, gap > 0): 3.6 of 5.5 carry nothing and receive nothing -- their
+// friction step would clamp to the empty cone and change no velocity. A lane therefore runs ahead over the idle records
+// of ITS list with the cheap part of the visit (is the accumulator empty -- bit j of `nz` -- and does the normal impulse
+// stay zero?) and the lanes of the warp only meet for the records that need the full visit: the number of full visits
+// per sweep is the largest number of ACTIVE contacts among the warp's samples, not the longest list.
+// `nz`: bit j = the accumulator of record j holds something (set at detection from the warm start, kept up to date here).
+// Returns the impulse on the links when WANT_SUM (cubeB's contacts are reported), else zero.
 template <bool WANT_SUM>
-DEV V3 solve_link_record(const float4* r, float4* lam_base, V3 ycol, float* slide, float ims_f, V3& v, V3& w, float im,
-                         float ii, float mu, bool first) {
-  const float4 q0 = r[0], q1 = r[1], q2 = r[2], q3 = r[3];
-  const V3 n = mk(q0.x, q0.y, q0.z), rc = mk(q1.x, q1.y, q1.z), vl0 = mk(q2.x, q2.y, q2.z), rcn = mk(q3.x, q3.y, q3.z);
-  const float target = q0.w, an = q1.w, ikn = q2.w;
-  const int meta = __float_as_int(q3.w), f = meta >> 24;
-  // link f: finger 1 slides along +y of the hand, finger 2 along -y, the hand box (f = 2) has no sliding DoF
-  const V3 axis = f == 0 ? ycol : (f == 1 ? -ycol : mk(0, 0, 0));
-  const float ims = f < 2 ? ims_f : 0.0f;
-  float sl = f == 1 ? slide[1] : slide[0];
-  float4* const Lp = lam_base + (meta & 0xffffff);
-  const float4 Lj = *Lp;
+DEV V3 walk_link_records(const float4* list, int n_own, unsigned& nz, float4* lam_base, V3 ycol, float* slide, float ims_f,
+                         V3& v, V3& w, float im, float ii, float mu, bool first) {
   V3 acc = mk(0, 0, 0);
-  if (first) {
-    const V3 Pw = Lj.x * n + mk(Lj.y, Lj.z, Lj.w);   // on the link; the cube receives -Pw
-    sl += ims * dot(axis, Pw);
-    v = v - im * Pw;
-    w = w - ii * cross(rc, Pw);
-    if (WANT_SUM) acc = Pw;
+  int j = 0;
+  for (;;) {
+    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+    bool found = false;
+    while (j < n_own) {
+      const float4* r = list + 4 * j;
+      q0 = r[0]; q1 = r[1]; q2 = r[2]; q3 = r[3];
+      if ((nz >> j) & 1u) { found = true; break; }
+      // empty accumulator: the visit does something only if the normal impulse becomes positive now
+      const int fq = __float_as_int(q3.w) >> 24;
+      const float slq = fq == 1 ? slide[1] : slide[0];
+      const V3 nq = mk(q0.x, q0.y, q0.z);
+      const float vnq = dot(mk(q2.x, q2.y, q2.z), nq) + slq * q1.w - (dot(v, nq) + dot(w, mk(q3.x, q3.y, q3.z)));
+      if (fmaxf((q0.w - vnq) * q2.w, 0.0f) != 0.0f) { found = true; break; }
+      ++j;
+    }
+    if (!__any_sync(kFull, found)) break;
+    if (found) {
+      const V3 n = mk(q0.x, q0.y, q0.z), rc = mk(q1.x, q1.y, q1.z), vl0 = mk(q2.x, q2.y, q2.z), rcn = mk(q3.x, q3.y, q3.z);
+      const float target = q0.w, an = q1.w, ikn = q2.w;
+      const int meta = __float_as_int(q3.w), f = meta >> 24;
+      // link f: finger 1 slides along +y of the hand, finger 2 along -y, the hand box (f = 2) has no sliding DoF
+      const V3 axis = f == 0 ? ycol : (f == 1 ? -ycol : mk(0, 0, 0));
+      const float ims = f < 2 ? ims_f : 0.0f;
+      float sl = f == 1 ? slide[1] : slide[0];
+      float4* const Lp = lam_base + (meta & 0xffffff);
+      const float4 Lj = *Lp;
+      if (first) {
+        const V3 Pw = Lj.x * n + mk(Lj.y, Lj.z, Lj.w);   // on the link; the cube receives -Pw
+        sl += ims * dot(axis, Pw);
+        v = v - im * Pw;
+        w = w - ii * cross(rc, Pw);
+        if (WANT_SUM) acc = acc + Pw;
+      }
+      const float vn0 = dot(vl0, n) + sl * an - (dot(v, n) + dot(w, rcn));
+      const float ln = fmaxf(Lj.x + (target - vn0) * ikn, 0.0f);
+      const float dj = ln - Lj.x;
+      sl += ims * an * dj;
+      v = v - (dj * im) * n;
+      w = w - (dj * ii) * rcn;
+      const V3 rv = (vl0 + sl * axis) - (v + cross(w, rc));
+      const float vn = dot(rv, n);
+      V3 t = rv - vn * n;
+      const float vt2 = dot(t, t);
+      V3 lt = mk(Lj.y, Lj.z, Lj.w);
+      if (vt2 >= 1e-18f) {
+        const float ivt = rsqrtf(vt2), vt = vt2 * ivt;
+        t = ivt * t;
+        const V3 rct = cross(rc, t);
+        const float at = dot(axis, t);
+        const float kt = ims * at * at + im + ii * dot(rct, rct);
+        lt = lt - __fdividef(vt, kt) * t;
+      }
+      const float lim = mu * ln, m2 = dot(lt, lt);
+      if (m2 > lim * lim) lt = (lim * rsqrtf(m2)) * lt;
+      const V3 Pt = lt - mk(Lj.y, Lj.z, Lj.w);
+      sl += ims * dot(axis, Pt);
+      v = v - im * Pt;
+      w = w - ii * cross(rc, Pt);
+      *Lp = make_float4(ln, lt.x, lt.y, lt.z);
+      // (ln == 0 empties the cone: lt == 0 too)
+      nz = (ln != 0.0f || lt.x != 0.0f || lt.y != 0.0f || lt.z != 0.0f) ? (nz | (1u << j)) : (nz & ~(1u << j));
+      if (f == 0) slide[0] = sl;
+      if (f == 1) slide[1] = sl;
+      if (WANT_SUM) acc = acc + dj * n + Pt;
+      ++j;
+    }
   }
-  const float vn0 = dot(vl0, n) + sl * an - (dot(v, n) + dot(w, rcn));
-  const float ln = fmaxf(Lj.x + (target - vn0) * ikn, 0.0f);
-  const float dj = ln - Lj.x;
-  if (ln == 0.0f && Lj.x == 0.0f && Lj.y == 0.0f && Lj.z == 0.0f && Lj.w == 0.0f) {
-    // an open (speculative) contact that carries nothing and receives nothing: the friction step below would clamp its
-    // impulse to the empty cone and change no velocity -- 3.6 of the 5.5 contacts of a grasp are of this kind
-    return acc;
-  }
-  sl += ims * an * dj;
-  v = v - (dj * im) * n;
-  w = w - (dj * ii) * rcn;
-  const V3 rv = (vl0 + sl * axis) - (v + cross(w, rc));
-  const float vn = dot(rv, n);
-  V3 t = rv - vn * n;
-  const float vt2 = dot(t, t);
-  V3 lt = mk(Lj.y, Lj.z, Lj.w);
-  if (vt2 >= 1e-18f) {
-    const float ivt = rsqrtf(vt2), vt = vt2 * ivt;
-    t = ivt * t;
-    const V3 rct = cross(rc, t);
-    const float at = dot(axis, t);
-    const float kt = ims * at * at + im + ii * dot(rct, rct);
-    lt = lt - __fdividef(vt, kt) * t;
-  }
-  const float lim = mu * ln, m2 = dot(lt, lt);
-  if (m2 > lim * lim) lt = (lim * rsqrtf(m2)) * lt;
-  const V3 Pt = lt - mk(Lj.y, Lj.z, Lj.w);
-  sl += ims * dot(axis, Pt);
-  v = v - im * Pt;
-  w = w - ii * cross(rc, Pt);
-  *Lp = make_float4(ln, lt.x, lt.y, lt.z);
-  if (f == 0) slide[0] = sl;
-  if (f == 1) slide[1] = sl;
-  if (WANT_SUM) acc = acc + dj * n + Pt;
   return acc;
 }
 
@@ -894,6 +918,7 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
     // cube (shared memory). Both groups detect at the same time (group g: link f against cube g); the serial order
     // only matters for the solves below.
     int nrec = 0;                  // records in the list of the own cube
+    unsigned nz = 0u;              // bit j: the accumulator of record j of that list holds something
     unsigned nmax[2] = {0u, 0u};   // warp-uniform: longest list of cubeA / cubeB in the warp
     const bool any_link = __any_sync(kFull, lnear != 0u);
     if (any_link) {
@@ -933,7 +958,9 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
               // previous sub-step of this step, applied by the slot's first visit below
               const int slot = f * (2 * CPL) + phs;
               float4* Ls = slam + slot * blockDim.x;
-              *Ls = warm_prepare(*Ls, (prev_lk >> slot) & 1u, lh.n, mu, P.warm_start);
+              const float4 Lw = warm_prepare(*Ls, (prev_lk >> slot) & 1u, lh.n, mu, P.warm_start);
+              *Ls = Lw;
+              if (Lw.x != 0.0f || Lw.y != 0.0f || Lw.z != 0.0f || Lw.w != 0.0f) nz |= 1u << pos;
               cur_lk |= 1u << slot;
               float4* r = srec + 4 * pos;
               r[0] = make_float4(lh.n.x, lh.n.y, lh.n.z, lh.target);
@@ -947,6 +974,8 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
       }
       // longest list of cubeA / cubeB in the warp: the bounds of the (warp-uniform) loops of the sweeps
       nrec = cnt;
+#pragma unroll
+      for (int o = 1; o < G; o <<= 1) nz |= __shfl_xor_sync(kFull, nz, o);   // the group's records, known to its first lane
       nmax[0] = __reduce_max_sync(kFull, g == 0 ? (unsigned)cnt : 0u);
       nmax[1] = __reduce_max_sync(kFull, g == 1 ? (unsigned)cnt : 0u);
       __syncwarp();   // records and prepared accumulators are read by the other lanes of the group
@@ -967,21 +996,14 @@ DEV void team_rollout(const RolloutCfg& c, const PandaParams& P, const RolloutBu
           const bool first = p == 0 && sw == 0;
           if (nmax[0]) {
             const int lead = t.team_base;
-            const bool mine = t.lane == lead;
-#pragma unroll 1
-            for (int j = 0; j < (int)nmax[0]; ++j)
-              if (mine && j < nrec) (void)solve_link_record<false>(srec + 4 * j, slam_base, H.R.cy, slide, ims_f, v, w, im, ii, mu, first);
+            (void)walk_link_records<false>(srec, t.lane == lead ? nrec : 0, nz, slam_base, H.R.cy, slide, ims_f, v, w, im, ii, mu, first);
             const V3 vl = shfl3(v, lead), wl = shfl3(w, lead);
             if (g == 0) { v = vl; w = wl; }
             slide[0] = __shfl_sync(kFull, slide[0], lead); slide[1] = __shfl_sync(kFull, slide[1], lead);
           }
           if (nmax[1]) {
             const int lead = t.team_base + G;
-            const bool mine = t.lane == lead;
-            V3 got = mk(0, 0, 0);
-#pragma unroll 1
-            for (int j = 0; j < (int)nmax[1]; ++j)
-              if (mine && j < nrec) got = got + solve_link_record<true>(srec + 4 * j, slam_base, H.R.cy, slide, ims_f, v, w, im, ii, mu, first);
+            V3 got = walk_link_records<true>(srec, t.lane == lead ? nrec : 0, nz, slam_base, H.R.cy, slide, ims_f, v, w, im, ii, mu, first);
             const V3 vl = shfl3(v, lead), wl = shfl3(w, lead);
             got = shfl3(got, lead);
             if (g == 1) { v = vl; w = wl; imp_cubeb = imp_cubeb - got; }
