@@ -155,7 +155,8 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-NCU_SUMMARY = {"c4": "r02_ncu_rollout_team_c4_summary.csv", "c4_grasp": "r02_ncu_rollout_team_grasp_summary.csv"}
+NCU_SUMMARY = {"c4": "r02_ncu_rollout_far_c4_summary.csv", "c5": "r02_ncu_rollout_far_c5_summary.csv",
+               "c4_grasp": "r02_ncu_rollout_team_grasp_summary.csv"}
 
 
 def ncu_numbers(name):
@@ -380,6 +381,7 @@ def main():
         wait_p.append(info.peer_wait_ms[1])
     last = planner.command_resident(sync=True)
     launches_per_step, lanes = last.launches, int(last.rollout_lanes)
+    near = int(last.near_samples)   # samples the far-field kernel left to the full rollout kernel (-1: it did not run)
     beta_iters = int(last.beta_iters)
     barrier()
 
@@ -470,6 +472,9 @@ def main():
         achieved = b_roll * K * T / (r_ms * 1e-3) / 1e9
         traffic, issue = ncu_numbers(name)
         kernel = (f"k_rollout_team (panda_env, {lanes} lanes per sample)" if lanes > 1 else f"k_rollout<{env}> (thread per sample)")
+        if near >= 0:
+            kernel = (f"k_rollout_far (panda_env, far-field samples, 16 lanes per sample) + {kernel} over the near list "
+                      f"({near} of {K} samples of this command)")
         line = {
             "metric": "sample-steps/sec (K x H per command)", "value": Kg * T / (ms_per_step * 1e-3),
             "unit": "sample-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -500,6 +505,12 @@ def main():
                          "note": "issue/latency-bound, not HBM-bound: the outputs stay in the 126 MB L2 (DRAM traffic < "
                                  "algorithmic bytes); see DESIGN.md 5"},
         }
+        if near >= 0:
+            line["far_field"] = {"near_samples": near, "far_samples": K - near,
+                                 "note": "rank 0, last command: samples whose gripper never comes within contact range of a cube, the "
+                                         "table or the shelf are rolled out by k_rollout_far (joints + geometry tests + cost only; exact: "
+                                         "the full path would skip the same work step by step); the others by the full rollout kernel "
+                                         "from their hand-over boundary. bench.py --config c4_grasp is the all-near case"}
         if n1_default is not None:
             line["n1_default_workload_at_this_n"] = n1_default
         if n1_same is not None:

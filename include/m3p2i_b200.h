@@ -245,6 +245,8 @@ typedef struct M3P2ICommandInfo {
   float peer_wait_ms[2]; /* sharded over peer memory: device time this rank spent waiting for [0] the discounted costs of
                             all ranks (start of the softmin kernel: rollout skew between ranks + the NVLink stores) and
                             [1] the partial sums of all ranks (end of the weighted-sum kernel); 0 when unsharded */
+  int32_t near_samples;  /* panda_env: samples of this shard the far-field kernel left to the full rollout kernel (the others
+                            never came near a cube, the table or the shelf and were finished by it); -1: it did not run */
 } M3P2ICommandInfo;
 
 typedef struct M3P2IHandle_* m3p2i_handle;

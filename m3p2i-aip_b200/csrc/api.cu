@@ -112,6 +112,7 @@ struct M3P2IHandle_ {
   DevBuf<int> near_list, near_count, far_info;   // far-field split (panda_far.cuh): rows left for the full rollout, two counters
   DevBuf<float> far_dump;                        // joint states of those rows at their hand-over boundaries
   unsigned far_epoch = 0;
+  const int* near_count_used = nullptr;   // counter of the last rollout's far-field split (nullptr: it did not run)
   DevBuf<Stats> stats;
   DevBuf<M3P2ICommandInfo> info;
   bool have_noise = false, have_row0 = false, have_filt = false, have_evr = false;
@@ -332,13 +333,19 @@ UpdateCfg make_ucfg(const H* h, int shift) {
   return u;
 }
 
+// one rank owns every sample: the shard's discounted costs ARE the global ones (no gather, no copy)
+bool local_is_global(const H* h) {
+  return h->cfg.num_samples == h->cfg.num_samples_global && (h->nranks == 1 || !h->comm);
+}
+
 UpdateBufs make_ubufs(const H* h) {
   UpdateBufs b;
-  b.J_global = h->J_global.p; b.weights = h->weights.p; b.stats = h->stats.p; b.actions = h->actions.p;
+  b.J_global = local_is_global(h) ? h->J.p : h->J_global.p; b.weights = h->weights.p; b.stats = h->stats.p; b.actions = h->actions.p;
   b.cost_sum = h->cost_sum.p; b.partials = h->partials.p; b.seq = h->seq.p; b.filt = h->have_filt ? h->filt.p : nullptr;
   b.cost_total = h->cost_total.p; b.result = h->result.p; b.info = h->info.p;
   b.host_result = h->mirror_dev;
   b.host_info = h->mirror_dev ? reinterpret_cast<M3P2ICommandInfo*>(h->mirror_dev + 2 * (size_t)h->cfg.horizon * h->cfg.nu) : nullptr;
+  b.near_count = h->near_count_used;
   b.done_counter = h->ref_flags.p + 2;
   b.stats_scratch = h->ref_flags.p + 8;
   memset(&b.peer, 0, sizeof(b.peer));
@@ -348,7 +355,7 @@ UpdateBufs make_ubufs(const H* h) {
 // where the gathered discounted costs of the last command live
 const float* j_global_ptr(const H* h) {
   if (h->peer_on && h->nranks > 1 && h->peer_epoch) return h->mailbox + (h->peer_epoch & 1u) * mailbox_layout(h).stride;
-  return h->J_global.p;
+  return local_is_global(h) ? h->J.p : h->J_global.p;
 }
 
 bool needs_refs(const H* h) { return h->cfg.env_type == M3P2I_ENV_PANDA && h->task == M3P2I_TASK_REACH; }
@@ -395,7 +402,8 @@ int run_rollout(H* h, int* launches, const float* actions_in_dev, bool push_peer
     b.near_count = h->near_count.p + (h->far_epoch & 1u);
     b.near_count_next = h->near_count.p + ((h->far_epoch + 1u) & 1u);
     b.far_info = h->far_info.p; b.far_dump = h->far_dump.p;
-    if (far_rollout_applies(h->cfg.env_type, c, b, refs)) ++h->far_epoch;
+    if (far_rollout_applies(h->cfg.env_type, c, b, refs)) { ++h->far_epoch; h->near_count_used = b.near_count; }
+    else h->near_count_used = nullptr;
   }
   launch_rollout(h->cfg.env_type, c, &h->pp, &h->qp, b, refs, h->stream, launches);
   CK(cudaGetLastError());
@@ -430,8 +438,7 @@ int gather_J(H* h) {
   if (h->nranks == 1 || !h->comm) {
     if (h->cfg.num_samples != h->cfg.num_samples_global)
       return fail(M3P2I_ERR_STATE, "sharded handle without a communicator: use the m3p2i_phase_* calls or m3p2i_comm_init");
-    CK(cudaMemcpyAsync(h->J_global.p, h->J.p, sizeof(float) * K, cudaMemcpyDeviceToDevice, h->stream));
-    return 0;
+    return 0;   // make_ubufs reads the costs where the rollout left them
   }
   ncclResult_t r = g_nccl.AllGather(h->J.p, h->J_global.p, K, ncclFloat, h->comm, h->stream);
   if (r != ncclSuccess) return fail(M3P2I_ERR_NCCL, std::string("ncclAllGather: ") + g_nccl.GetErrorString(r));
@@ -1221,7 +1228,8 @@ int m3p2i_phase_rollout(m3p2i_handle h, float* out_J_local) {
 int m3p2i_phase_partials(m3p2i_handle h, const float* J_global, float* out_partials) {
   if (!h || !J_global || !out_partials) return fail(M3P2I_ERR_ARG, "null argument");
   const size_t n = 7 * (size_t)h->cfg.horizon * h->cfg.nu + 1;
-  CK(cudaMemcpyAsync(h->J_global.p, J_global, sizeof(float) * h->cfg.num_samples_global, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(local_is_global(h) ? h->J.p : h->J_global.p, J_global, sizeof(float) * h->cfg.num_samples_global,
+                     cudaMemcpyHostToDevice, h->stream));
   int launches = 0, rc;
   if ((rc = run_update(h, 1, &launches))) return rc;
   h->last_info.launches += launches;

@@ -698,6 +698,7 @@ DEV void finish_body(const UpdateCfg& u, const UpdateBufs& b, float* smean /* sh
     in->mean_cost_sum = mean_cost;
     in->beta_iters = S->beta_iters;
     in->peer_wait_ms[0] = S->peer_wait_ms[0]; in->peer_wait_ms[1] = S->peer_wait_ms[1];
+    in->near_samples = b.near_count ? __ldcg(b.near_count) : -1;
     if (b.host_info) *b.host_info = *in;
   }
 }

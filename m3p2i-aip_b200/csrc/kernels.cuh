@@ -42,6 +42,7 @@ struct UpdateBufs {
   M3P2ICommandInfo* info;  // device copy
   float* host_result;      // the same two rows in mapped pinned host memory (written by the kernel: no D2H copy)
   M3P2ICommandInfo* host_info;
+  const int* near_count;   // this command's counter of the far-field split (panda_far.cuh) or nullptr: reported in the info
   unsigned* done_counter;  // CTA completion counter of the fused wsum + finish launch
   unsigned* stats_scratch; // [0] CTA completion counter of the multi-modal k_stats, [1..3] beta iterations per set
   PeerReduce peer;

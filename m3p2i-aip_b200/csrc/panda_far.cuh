@@ -34,7 +34,7 @@ constexpr int kFarBlockMax = 480;             // 14 sample warps + the warp of t
 // floats of shared memory per sample: actions [T][9], joint positions [n_iter + 1][8] (7 arm joints + pad),
 // finger openings [n_iter + 1][2], costs [T]; rounded so that consecutive samples start in different banks
 __host__ __device__ inline int far_sample_floats(int T, int ns) {
-  const int n = 9 * T + 10 * (T * ns + 1) + T + 9 * (T * ns / 8 + 1);
+  const int n = 9 * T + 10 * (T * ns + 1) + T + 16 * (T * ns / 8 + 1);
   return (n + 3) / 4 * 4 + 4;
 }
 
@@ -92,7 +92,7 @@ DEV bool far_team_eval(const RolloutCfg& c, const PandaParams& P, const RolloutB
   float* const sq = su + 9 * T;                                       // [n_iter + 1][8]
   float* const sf = sq + 8 * (n_iter + 1);                            // [n_iter + 1][2]
   float* const sc = sf + 2 * (n_iter + 1);                            // [T]
-  float* const sbv = sc + T;                                          // [n_iter / 8 + 1][9] velocities at the boundaries
+  float* const sbv = sc + T;                                          // [n_iter / 8 + 1][16] velocities at the boundaries
 
   // pass 0: the tests of iteration 0 alone (the start state's joint positions, the same for every sample): when the gripper
   // starts next to a cube or the table, nothing of this launch is far and the three phases are not worth running
@@ -119,29 +119,35 @@ DEV bool far_team_eval(const RolloutCfg& c, const PandaParams& P, const RolloutB
   __syncwarp();
 
   // ---- 2. the nine joints through the horizon (lane j: joint j; the arithmetic of the team kernel's run-ahead / finger
-  // drives). sq / sf keep the position every iteration sees, entry n_iter the final one.
+  // drives). sq / sf keep the position every iteration sees, entry n_iter the final one. Lanes 9-15 shadow the second
+  // finger and write into the pad column of sq / the spare columns of sbv, so that the loop has no lane predicates;
+  // all addresses are running pointers.
   {
     const int jo = min(tl, 8);
-    const bool arm = jo < 7, mine = tl < 9;
+    const bool arm = jo < 7;
     float qo = c.base_env[2 * jo], vo = c.base_env[2 * jo + 1];
     const float lo_o = P.q_lower[jo], up_o = P.q_upper[jo], vl_o = P.qd_limit[jo], ef_o = P.effort[jo];
     const float m = arm ? P.joint_inertia[min(jo, 6)] : P.finger_mass;
-    float* const dst = arm ? sq + jo : sf + (jo - 7);
-    const int stride = arm ? 8 : 2;
+    const float hD = h * D, den = m + h * D, kick = h * ef_o / m;
+    float* pq = arm ? sq + jo : (tl < 9 ? sf + (jo - 7) : sq + 7);
+    const int stride = (arm || tl >= 9) ? 8 : 2;
+    float* pv = sbv + tl;
+    const float* pu = su + jo;
+    float4* ps = valid && tl == 0 ? b.states + k : nullptr;
     float uj = 0.0f;
 #pragma unroll 1
-    for (int it = 0, step = 0, s = 0; it < n_iter; ++it) {
-      if (s == 0) uj = su[step * NU + jo];
-      if ((it & 7) == 0 && mine) sbv[(it >> 3) * 9 + jo] = vo;
-      float vs = (m * vo + h * D * uj) / (m + h * D);
+    for (int it = 0, s = 0; it < n_iter; ++it) {
+      if (s == 0) { uj = *pu; pu += NU; }
+      if ((it & 7) == 0) { *pv = vo; pv += 16; }
+      float vs = (m * vo + hD * uj) / den;
       const float f = D * (uj - vs);
-      if (f > ef_o) vs = vo + h * ef_o / m;
-      else if (f < -ef_o) vs = vo - h * ef_o / m;
+      if (f > ef_o) vs = vo + kick;
+      else if (f < -ef_o) vs = vo - kick;
       vs = clampf(vs, -vl_o, vl_o);
       if (qo <= lo_o && vs < 0.0f) vs = 0.0f;
       if (qo >= up_o && vs > 0.0f) vs = 0.0f;
       vo = vs;
-      if (mine) dst[it * stride] = qo;
+      *pq = qo; pq += stride;
       float qn = qo + h * vo;
       if (qn < lo_o) { qn = lo_o; vo = 0.0f; }
       if (qn > up_o) { qn = up_o; vo = 0.0f; }
@@ -149,12 +155,12 @@ DEV bool far_team_eval(const RolloutCfg& c, const PandaParams& P, const RolloutB
       if (++s == ns) {
         // state row of the finished step (q1, qd1, q2, qd2; reactive_tamp.py:66-69)
         const float q2 = __shfl_sync(kFull, qo, team_base + 1), v2 = __shfl_sync(kFull, vo, team_base + 1);
-        if (valid && tl == 0) b.states[(size_t)step * K + k] = make_float4(qo, vo, q2, v2);
-        s = 0; ++step;
+        if (ps) { *ps = make_float4(qo, vo, q2, v2); ps += K; }
+        s = 0;
       }
     }
-    if (mine) dst[n_iter * stride] = qo;
-    if ((n_iter & 7) == 0 && mine) sbv[(n_iter >> 3) * 9 + jo] = vo;
+    *pq = qo;
+    if ((n_iter & 7) == 0) *pv = vo;
   }
   __syncwarp();
   }   // pass 1
@@ -181,11 +187,15 @@ DEV bool far_team_eval(const RolloutCfg& c, const PandaParams& P, const RolloutB
   const int ls = 31 - __clz(ns);   // ns is a power of two (checked by the launcher)
 #pragma unroll 1
   for (int i = pass == 0 ? 0 : tl; i <= (pass == 0 ? 0 : n_iter); i += TM) {
-    float sn[7], cs[7], qd0[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) { sincosf(sq[i * 8 + j], &sn[j], &cs[j]); qd0[j] = 0.0f; }
     Hand H;
-    fk_from_sincos(P, sn, cs, qd0, H);
+    H.p = mk(0, 0, 0); H.R.cx = mk(1, 0, 0); H.R.cy = mk(0, 1, 0); H.R.cz = mk(0, 0, 1); H.v = mk(0, 0, 0); H.w = mk(0, 0, 0);
+    if (i < n_iter || c.task != M3P2I_TASK_PICK) {   // (the pick cost does not read the hand pose: panda_cost)
+      float sn[7], cs[7], qd0[7];
+      const float* pq = sq + i * 8;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) { sincosf(pq[j], &sn[j], &cs[j]); qd0[j] = 0.0f; }
+      fk_from_sincos(P, sn, cs, qd0, H);
+    }
     const float q7 = sf[i * 2], q8 = sf[i * 2 + 1];
     if (i < n_iter) {
       V3 ll[3];
@@ -292,7 +302,7 @@ DEV bool far_team_eval(const RolloutCfg& c, const PandaParams& P, const RolloutB
       const int bi = idx / 9, j = idx - bi * 9, it = bi * 8;
       float* d = b.far_dump + ((size_t)k * nb + bi) * 18 + 2 * j;
       d[0] = j < 7 ? sq[it * 8 + j] : sf[it * 2 + (j - 7)];
-      d[1] = sbv[bi * 9 + j];
+      d[1] = sbv[bi * 16 + j];
     }
   }
   return team_ok;

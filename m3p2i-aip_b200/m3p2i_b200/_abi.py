@@ -84,7 +84,7 @@ class CommandInfo(C.Structure):
     _fields_ = [
         ("eta", f32 * 3), ("beta", f32 * 3), ("min_cost", f32 * 3), ("best_idx", i32 * 3),
         ("weight_push", f32), ("weight_pull", f32), ("mean_cost_sum", f32), ("kernel_ms", f32),
-        ("launches", i32), ("beta_iters", i32), ("rollout_ms", f32), ("rollout_lanes", i32), ("peer_wait_ms", f32 * 2),
+        ("launches", i32), ("beta_iters", i32), ("rollout_ms", f32), ("rollout_lanes", i32), ("peer_wait_ms", f32 * 2), ("near_samples", i32),
     ]
 
 

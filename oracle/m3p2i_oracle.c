@@ -422,6 +422,7 @@ static void o_compute_stats(Oracle* o) {
   const float* J = o->J_global;
   M3P2ICommandInfo* in = &o->info;
   memset(in, 0, sizeof(*in));
+  in->near_samples = -1;   /* the oracle has no far-field split: every sample takes the full rollout */
   int lo[3] = {0, 0, half}, n[3] = {Kg, half, Kg - half};
   int nsets = c->multi_modal ? 3 : 1;
   for (int s = 0; s < nsets; ++s) {
