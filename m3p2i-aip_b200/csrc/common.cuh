@@ -75,6 +75,10 @@ struct RolloutCfg {
   unsigned epoch;   // ref_flags reach epoch + t + 1 when step t of this launch has been published
   int align;        // team kernel: 1 = re-align the CTA's warps with a barrier every sub-step (I-cache sharing)
   int lanes;        // lanes per sample: 1 = one thread per sample, 16 = lane-cooperative team (panda_env)
+  // large K behind the far-field kernel: both rollout kernels are launched over the near list and the count decides on the
+  // device which one works -- the team kernel up to near_team_max samples (0: no limit), the thread-per-sample kernel
+  // above near_thread_min - 1 (0: always)
+  int near_team_max, near_thread_min;
   float dt, gamma, u_scale, kp_suction, pre_height_diff, tilt_cos;
   float u_min[kMaxNu], u_max[kMaxNu], sigma[kMaxNu];
   float goal[8];

@@ -67,6 +67,7 @@ k_rollout(const __grid_constant__ RolloutCfg c, const __grid_constant__ typename
   const bool listed = ENV == M3P2I_ENV_PANDA && b.near_list != nullptr;
   int count = c.K;
   if (listed) count = __ldcg(b.near_count);
+  if (listed && count < c.near_thread_min) return;   // few samples left: the team kernel launched before this one took them
   if (use_refs && blockIdx.x == 0) {
     // (rows that stayed in the far field were published by k_rollout_far)
     if (ENV == M3P2I_ENV_PANDA && count > 0 && !(listed && __ldcg(b.far_info + 2))) produce_refs(c, P, b, threadIdx.x);
@@ -311,6 +312,33 @@ void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, co
   const int block = rollout_block(c.K);
   const int extra = need_refs ? 1 : 0;   // CTA 0 = producer of the batch rows every reach cost reads
   const int grid = (c.K + block - 1) / block + extra;
+  if (env_type == M3P2I_ENV_PANDA && c.lanes == 1 && b.near_list && c.K > 84 * team_sms()) {
+    // K beyond the team kernel's range, but the far-field kernel has usually left only a few samples: launch the team
+    // kernel for up to kTeamMax listed samples and the thread-per-sample kernel for more; the count decides on the device
+    const int kTeamMax = 84 * team_sms();
+    RolloutCfg ct = c;
+    ct.lanes = 8; ct.near_team_max = kTeamMax;
+    RolloutBufs bt = b;
+    // (a K-sample launch shape with K = kTeamMax: CTAs beyond the count leave at once)
+    ct.K = c.K;
+    const int tb = team_block(kTeamMax, extra, 4);
+    const int tgrid = (kTeamMax + tb / 8 - 1) / (tb / 8) + extra;
+    const size_t smem = (size_t)7 * 2 * sizeof(float4) * tb + (size_t)(tb / 8) * 2 * kRecStride * sizeof(float4) +
+                        (need_refs ? (size_t)(tb / 8) * 2 * c.T * sizeof(float4) : 0);
+    if (first_use_on_device(0)) {
+      const int max_smem = 7 * 2 * (int)sizeof(float4) * kTeamBlockMax +
+                           (kTeamBlockMax / 8) * 2 * (kRecStride + kMaxT) * (int)sizeof(float4);
+      cudaFuncSetAttribute(k_rollout_team<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      cudaFuncSetAttribute(k_rollout_team<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    }
+    k_rollout_team<2><<<tgrid, tb, smem, st>>>(ct, *qp, bt);
+    ++*launches;
+    RolloutCfg c1 = c;
+    c1.near_thread_min = kTeamMax + 1;
+    k_rollout<M3P2I_ENV_PANDA><<<grid, block, 0, st>>>(c1, *qp, b);
+    ++*launches;
+    return;
+  }
   if (env_type == M3P2I_ENV_POINT) {
     k_rollout<M3P2I_ENV_POINT><<<grid, block, 0, st>>>(c, *pp, b);
   } else if (c.lanes == 16 || c.lanes == 8) {

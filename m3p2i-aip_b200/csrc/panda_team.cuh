@@ -1210,6 +1210,7 @@ DEV void team_kernel_body(const RolloutCfg& c, const PandaParams& P, const Rollo
   if (b.near_list) count = __ldcg(b.near_count);
   const int cta_first = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x) / TM;
   if (count <= 0 || (!producer && cta_first >= count)) return;
+  if (c.near_team_max > 0 && count > c.near_team_max) return;   // the thread-per-sample kernel takes this one
   if (producer && b.near_list && __ldcg(b.far_info + 2)) return;   // k_rollout_far published the rows (they stayed far)
   const int kraw = ((blockIdx.x - (use_refs ? 1 : 0)) * blockDim.x + threadIdx.x) / TM;
   const bool valid = !producer && kraw < count;

@@ -273,7 +273,9 @@ def test_far_field_split_matches_full_rollout(monkeypatch, task, mm, shelf, lift
         res[far] = out
         n.close()
     for i, ((a1, c1, ch1, st1, ac1, l1), (a0, c0, ch0, st0, ac0, l0)) in enumerate(zip(res["1"], res["0"])):
-        assert l1 == l0 + 1   # one more launch: the far-field kernel
+        # one more launch, the far-field kernel; beyond the team kernel's range (K > 84 SMs) two: team AND thread-per-sample
+        # kernel are launched over the near list and its length decides on the device which one works
+        assert l1 == l0 + (2 if K > 12432 else 1)
         if i == 0:
             assert np.array_equal(ac1, ac0) and np.array_equal(st1, st0)   # same planner state: same actions, same joints
         else:
