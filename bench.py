@@ -389,12 +389,12 @@ def main():
     n_e2e = args.steps
     for _ in range(3):
         planner.set_state(dof, root)
-        planner.command(want_cost=False)
+        planner.command(want_cost=False, want_info=False)
     barrier()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
         planner.set_state(dof, root)                      # pinned staging + H2D inside
-        act, _, _ = planner.command(want_cost=False)      # D2H of the action inside, synchronous
+        act, _, _ = planner.command(want_cost=False, want_info=False)   # D2H of the action inside, synchronous
     barrier()
     t_timed1 = time.perf_counter()
     e2e_s = torch.tensor([(t_timed1 - t0) / n_e2e], dtype=torch.float64, device="cuda")

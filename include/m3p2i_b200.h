@@ -296,7 +296,8 @@ int m3p2i_set_planner_state(m3p2i_handle h, const M3P2IPlannerState* in);
 int m3p2i_set_filter_matrix(m3p2i_handle h, const float* S);
 
 /* One planner tick. out_action: [T,nu]; out_cost_total: [K_local] or NULL (mppi.py:325 quirk included);
- * info may be NULL. */
+ * info may be NULL: the command then records no timing events on the stream (kernel_ms / rollout_ms are only measured
+ * for callers that ask for the scalars). */
 int m3p2i_command(m3p2i_handle h, float* out_action, float* out_cost_total, M3P2ICommandInfo* info);
 
 /* Same tick without any host<->device copy of inputs or results (state, means stay resident);

@@ -116,6 +116,8 @@ struct M3P2IHandle_ {
   DevBuf<Stats> stats;
   DevBuf<M3P2ICommandInfo> info;
   bool have_noise = false, have_row0 = false, have_filt = false, have_evr = false;
+  bool timed = false;   // the last command recorded its timing events (a caller that does not ask for the info scalars
+                        // gets none: three event records less on the stream, k_stats overlaps the rollout's tail)
   // pinned host staging: results (grows on demand) and, separately, the packed base env written by set_state and
   // uploaded lazily (it must survive a reallocation of the result buffer)
   float* pin = nullptr;
@@ -494,16 +496,20 @@ int fetch(H* h, float* out_action, float* out_cost_total, M3P2ICommandInfo* info
   return 0;
 }
 
-int command_device(H* h) {
+int command_device(H* h, bool timed) {
   int rc = check_ready(h);
   if (rc) return rc;
   int launches = 0;
-  CK(cudaEventRecord(h->ev0, h->stream));
+  h->timed = timed;
+  h->have_evr = false;
+  if (timed) CK(cudaEventRecord(h->ev0, h->stream));
   const bool peers = h->peer_on && h->nranks > 1;   // exchange fused into the kernels over peer memory
   if (peers) ++h->peer_epoch;
   if ((rc = run_rollout(h, &launches, nullptr, peers))) return rc;
-  CK(cudaEventRecord(h->evr, h->stream));
-  h->have_evr = true;
+  if (timed) {
+    CK(cudaEventRecord(h->evr, h->stream));
+    h->have_evr = true;
+  }
   if (!peers && (rc = gather_J(h))) return rc;
   const bool fused = peers || h->nranks == 1 || !h->comm;   // no host-visible exchange between sums and mean update
   if ((rc = run_update(h, 1, &launches, fused))) return rc;
@@ -511,13 +517,18 @@ int command_device(H* h) {
     if ((rc = reduce_partials(h))) return rc;
     if ((rc = run_finish(h, 1, &launches))) return rc;
   }
-  CK(cudaEventRecord(h->ev1, h->stream));
+  if (timed) CK(cudaEventRecord(h->ev1, h->stream));
   h->last_info.launches = launches;
   return 0;
 }
 
 int finish_timing(H* h) {
   float ms = 0.0f;
+  h->last_info.rollout_lanes = rollout_lanes(h);
+  if (!h->timed) {
+    h->last_info.kernel_ms = 0.0f; h->last_info.rollout_ms = 0.0f;
+    return 0;
+  }
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_info.kernel_ms = ms;
   h->last_info.rollout_lanes = rollout_lanes(h);
@@ -905,7 +916,7 @@ int m3p2i_set_filter_matrix(m3p2i_handle h, const float* S) {
 }
 
 int m3p2i_command(m3p2i_handle h, float* out_action, float* out_cost_total, M3P2ICommandInfo* info) {
-  int rc = command_device(h);
+  int rc = command_device(h, info != nullptr);
   if (rc) return rc;
   if ((rc = fetch(h, out_action, out_cost_total, nullptr, false))) return rc;
   if ((rc = finish_timing(h))) return rc;
@@ -914,7 +925,7 @@ int m3p2i_command(m3p2i_handle h, float* out_action, float* out_cost_total, M3P2
 }
 
 int m3p2i_command_resident(m3p2i_handle h, M3P2ICommandInfo* info) {
-  int rc = command_device(h);
+  int rc = command_device(h, info != nullptr);
   if (rc) return rc;
   if (info) {  // asking for the scalars forces a sync; pass NULL to keep the stream running
     CK(cudaStreamSynchronize(h->stream));
@@ -981,6 +992,7 @@ int m3p2i_update_only(m3p2i_handle h, const float* cost_h, const float* actions,
   CK(cudaMemcpyAsync(h->scratch.p, cost_h, sizeof(float) * K * T, cudaMemcpyHostToDevice, h->stream));
   launch_transpose(h->scratch.p, h->cost_h.p, (int)K, (int)T, h->stream);
   int launches = 0, rc;
+  h->timed = true; h->have_evr = false;
   CK(cudaEventRecord(h->ev0, h->stream));
   launch_discount(h->cost_h.p, h->J.p, h->cost_sum.p, (int)K, (int)T, h->cfg.gamma, h->stream, &launches);
   if ((rc = gather_J(h))) return rc;
@@ -1216,6 +1228,7 @@ int m3p2i_phase_rollout(m3p2i_handle h, float* out_J_local) {
   int rc = check_ready(h);
   if (rc) return rc;
   int launches = 0;
+  h->timed = true; h->have_evr = false;
   CK(cudaEventRecord(h->ev0, h->stream));
   if ((rc = run_rollout(h, &launches, nullptr))) return rc;
   h->last_info.launches = launches;

@@ -291,7 +291,8 @@ bool far_rollout_applies(int env_type, const RolloutCfg& c, const RolloutBufs& b
   const bool enabled = env ? atoi(env) != 0 : true;
   if (!enabled || env_type != M3P2I_ENV_PANDA || c.env_live || c.store_env || !b.near_list) return false;
   if (c.K >= (1 << kFarRowBits)) return false;
-  if (c.substeps <= 0 || (c.substeps & (c.substeps - 1))) return false;
+  // hand-over boundaries are multiples of 8 iterations and must be step boundaries: 1, 2, 4 or 8 sub-steps
+  if (c.substeps <= 0 || c.substeps > 8 || (c.substeps & (c.substeps - 1))) return false;
   return far_sample_warps(c.K, c.T, c.substeps, need_refs ? 1 : 0, 200 * 1024) > 0;
 }
 

@@ -142,11 +142,12 @@ class NativePlanner:
         self._ck(self.fn["m3p2i_set_stream"](self.h, A.vp(cuda_stream or 0)), "m3p2i_set_stream")
 
     # ---------------------------------------------------------------- one tick
-    def command(self, want_cost=True):
-        """-> (action [T,nu], cost_total [K] or None, CommandInfo). Arrays are reused between calls."""
+    def command(self, want_cost=True, want_info=True):
+        """-> (action [T,nu], cost_total [K] or None, CommandInfo or None). Arrays are reused between calls.
+        want_info=False: no scalars and no timing events on the stream (the plain control loop)."""
         self._ck(self.fn["m3p2i_command"](self.h, A.as_fp(self._act), A.as_fp(self._cost) if want_cost else None,
-                                         C.byref(self._info)), "m3p2i_command")
-        return self._act, (self._cost if want_cost else None), self._info
+                                         C.byref(self._info) if want_info else None), "m3p2i_command")
+        return self._act, (self._cost if want_cost else None), (self._info if want_info else None)
 
     def command_resident(self, sync=False):
         self._ck(self.fn["m3p2i_command_resident"](self.h, C.byref(self._info) if sync else None),

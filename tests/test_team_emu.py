@@ -164,3 +164,22 @@ def _split_case(task, fingers, K, T, shelf, mm, lift, sigma, seed, lanes):
     assert np.allclose(cs, ch.sum(1), rtol=1e-5, atol=1e-4) and np.allclose(J, (ch * g).sum(1), rtol=1e-5, atol=1e-4)
     if task == "pick" and lift in (0.5, 0.6):
         assert far.any() and (~far).any() and (bd[~far] > 0).any()   # far samples, near samples and real hand-overs
+
+
+@pytest.mark.parametrize("task,T,ns", [("pick", 32, 1), ("pick", 32, 4), ("reach", 32, 4), ("pick", 36, 1), ("pick", 30, 2)])
+@pytest.mark.parametrize("lanes", [8, 16])
+def test_far_split_other_substeps_and_horizons(task, T, ns, lanes):
+    """Hand-over boundaries are multiples of 8 ITERATIONS: 1 and 4 sub-steps per step and horizons whose iteration count
+    is not a multiple of the run-ahead block (16) must hand over at step boundaries all the same."""
+    c, scene, task, goal, grip, dof, root, a, _, _ = _case(task, 0.04, 24, T, lift=0.45, sigma=1.5, seed=2)
+    c.substeps = ns
+    o = O.Oracle(c, scene)
+    o.set_state(dof, root)
+    o.set_objective(task, goal, grip)
+    st_o, ch_o = o.rollout_actions(a)
+    o.close()
+    st, ch, cs, J, far, bd = E.split_rollout_actions(c, scene, task, goal, grip, dof, root, a, lanes)
+    assert far.any() and (~far).any() and (bd[~far] > 0).all()
+    assert np.allclose(st, st_o, rtol=1e-5, atol=1e-5)
+    assert np.isclose(ch, ch_o, rtol=1e-3, atol=5e-3).all(), np.abs(ch - ch_o).max()
+    assert np.allclose(cs, ch.sum(1), rtol=1e-5, atol=1e-4)
