@@ -277,3 +277,40 @@ def test_wire_frames_are_safe_and_raw_frames_round_trip():
     torch.save(Evil(), buf)
     with pytest.raises(Exception):
         D.bytes_to_torch(buf.getvalue())
+
+
+def _decode_in_child(token, q):
+    import sys
+    sys.path[:0] = [p for p in sys.path]
+    from m3p2i_aip.utils import data_transfer as D
+    t = D.bytes_to_torch(token)
+    q.put((tuple(t.shape), float(t.sum())))
+
+
+def test_shared_memory_frames_cross_processes():
+    """the two processes of the loop on one host exchange a ~50-byte token; the fp32 payload stays in a named
+    shared-memory segment. Same decoder entry point as the reference's frames (bytes_to_torch); a token whose slot has
+    been reused is refused."""
+    import multiprocessing as mp
+    from m3p2i_aip.utils import data_transfer as D
+    ch = D.ShmFrames(slots=4, max_floats=4096)
+    try:
+        dof, root = torch.randn(1, 18), torch.randn(1, 7, 13)
+        tok_d, tok_r = ch.put(dof), ch.put(root)
+        assert len(tok_d) < 80
+        assert torch.equal(D.bytes_to_torch(tok_d), dof) and torch.equal(D.bytes_to_torch(tok_r), root)
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        p = ctx.Process(target=_decode_in_child, args=(tok_r, q))
+        p.start()
+        shape, total = q.get(timeout=120)
+        p.join(timeout=60)
+        assert shape == (1, 7, 13) and abs(total - float(root.sum())) < 1e-4
+        for _ in range(4):            # the ring wraps: the first tokens' slots are reused
+            ch.put(torch.zeros(3))
+        with pytest.raises(ValueError):
+            D.bytes_to_torch(tok_d)
+        with pytest.raises(ValueError):
+            ch.put(torch.zeros(5000))
+    finally:
+        ch.close()
