@@ -183,3 +183,42 @@ def test_far_split_other_substeps_and_horizons(task, T, ns, lanes):
     assert np.allclose(st, st_o, rtol=1e-5, atol=1e-5)
     assert np.isclose(ch, ch_o, rtol=1e-3, atol=5e-3).all(), np.abs(ch - ch_o).max()
     assert np.allclose(cs, ch.sum(1), rtol=1e-5, atol=1e-4)
+
+
+def _base_mods():
+    actors = S.default_actors("panda_env")
+    ia, ib = S.actor_index(actors, "cubeA"), S.actor_index(actors, "cubeB")
+
+    def lift(r): r[ia, 2] += 0.02
+    def moving(r): r[ia, 7] = 0.02
+    def creeping(r): r[ia, 7] = 0.003
+    def spinning(r): r[ia, 12] = 0.2
+    def tilted(r): r[ia, 3:7] = [np.sin(0.15), 0, 0, np.cos(0.15)]; r[ia, 2] += 0.01
+    def stacked(r): r[ia, :3] = r[ib, :3] + np.array([0, 0, 0.05], np.float32)
+    def touching(r): r[ia, :3] = r[ib, :3] + np.array([0.0505, 0, 0], np.float32)
+    def edge(r): r[ia, 0] = 0.58
+    def both(r): r[ia, 2] += 0.02; r[ib, 2] += 0.03
+    return {"rest": (lambda r: None, True), "lift": (lift, False), "moving": (moving, False), "creeping": (creeping, True),
+            "spinning": (spinning, False), "tilted": (tilted, False), "stacked": (stacked, False), "touching": (touching, False),
+            "edge": (edge, False), "both": (both, False)}
+
+
+@pytest.mark.parametrize("name", ["rest", "lift", "moving", "creeping", "spinning", "tilted", "stacked", "touching", "edge", "both"])
+def test_far_field_start_state_rule(name):
+    """far_base_asleep: the far-field code may only take a command whose cubes the full path would put to sleep in the very
+    first sub-step (at rest on their support, below the speed thresholds, not touching each other). Start states with a cube
+    in the air, moving, tilted, stacked, touching the other cube or hanging over the table edge must all go to the rollout
+    kernel -- and whatever is decided, every sample carries the oracle's costs."""
+    mod, expect_far = _base_mods()[name]
+    c, scene, task, goal, grip, dof, root, a, _, _ = _case("pick", None, 8, 16)
+    root = np.asarray(root, np.float32).reshape(-1, 13).copy()
+    mod(root)
+    o = O.Oracle(c, scene)
+    o.set_state(dof, root)
+    o.set_objective(task, goal, grip)
+    st_o, ch_o = o.rollout_actions(a)
+    o.close()
+    st, ch, cs, J, far, bd = E.split_rollout_actions(c, scene, task, goal, grip, dof, root, a, 8)
+    assert far.all() if expect_far else not far.any(), far
+    assert np.allclose(st, st_o, rtol=1e-5, atol=1e-5)
+    assert np.isclose(ch, ch_o, rtol=1e-3, atol=5e-3).all(), np.abs(ch - ch_o).max()
