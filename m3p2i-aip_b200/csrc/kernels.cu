@@ -129,6 +129,7 @@ template <int CPL>
 __global__ void __launch_bounds__(kTeamBlockMax, 1)
 k_rollout_team(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
   pdl_launch_dependents();   // k_stats may be set up while this grid runs; it waits for its completion (pdl_wait)
+  if (b.near_list) pdl_wait();   // behind k_rollout_far: its near list, dumps and costs must be complete and visible
   team_kernel_body<CPL>(c, P, b);
 }
 
@@ -137,6 +138,7 @@ k_rollout_team(const __grid_constant__ RolloutCfg c, const __grid_constant__ Pan
 // rollout kernel launched next (deterministic order inside a CTA, CTAs in the order of their atomic reservation).
 __global__ void __launch_bounds__(kFarBlockMax, 1)
 k_rollout_far(const __grid_constant__ RolloutCfg c, const __grid_constant__ PandaParams P, const RolloutBufs b) {
+  pdl_launch_dependents();   // the rollout kernel over the near list is set up while this grid runs (it waits in pdl_wait)
   M3_DYNAMIC_SMEM(float4, far_smem);
   __shared__ int s_prod_bad, s_near[kFarBlockMax / 32 + 1], s_base;
   const bool use_refs = b.refs != nullptr;
@@ -269,6 +271,18 @@ static int team_block(int K, int extra, int per_warp) {
   return 32 * best_w;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (host side)
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // shape of the far-field launch: sample warps per CTA (<= 14) that keeps the shared memory within `smem_cap` and spreads
 // the CTAs evenly over the SMs; 0 = the horizon does not fit
 static int far_sample_warps(int K, int T, int ns, int extra_warp, size_t smem_cap) {
@@ -332,7 +346,7 @@ void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, co
       cudaFuncSetAttribute(k_rollout_team<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
       cudaFuncSetAttribute(k_rollout_team<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     }
-    k_rollout_team<2><<<tgrid, tb, smem, st>>>(ct, *qp, bt);
+    launch_pdl(k_rollout_team<2>, dim3(tgrid), dim3(tb), smem, st, ct, *qp, bt);
     ++*launches;
     RolloutCfg c1 = c;
     c1.near_thread_min = kTeamMax + 1;
@@ -360,24 +374,16 @@ void launch_rollout(int env_type, const RolloutCfg& c, const PointParams* pp, co
       cudaFuncSetAttribute(k_rollout_team<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
       cudaFuncSetAttribute(k_rollout_team<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     }
-    if (c.lanes == 16) k_rollout_team<1><<<tgrid, tb, smem, st>>>(c, *qp, b);
+    if (b.near_list) {
+      // programmatic dependent launch behind k_rollout_far: the launch latency hides behind that kernel
+      if (c.lanes == 16) launch_pdl(k_rollout_team<1>, dim3(tgrid), dim3(tb), smem, st, c, *qp, b);
+      else launch_pdl(k_rollout_team<2>, dim3(tgrid), dim3(tb), smem, st, c, *qp, b);
+    } else if (c.lanes == 16) k_rollout_team<1><<<tgrid, tb, smem, st>>>(c, *qp, b);
     else k_rollout_team<2><<<tgrid, tb, smem, st>>>(c, *qp, b);
   } else {
     k_rollout<M3P2I_ENV_PANDA><<<grid, block, 0, st>>>(c, *qp, b);
   }
   ++*launches;
-}
-
-// ------------------------------------------------------------------ programmatic dependent launch (host side)
-template <typename... KArgs, typename... Args>
-static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // ------------------------------------------------------------------ block reductions (fixed order => reproducible)
