@@ -459,6 +459,34 @@ def main():
                               "way and timed the same way (device events, max over ranks, L2 flushed)"}
         p4.close()
         barrier()
+    # N = 1 default line: the same command in the CONTACT-RICH state of the same config (fingers closed around cubeA: every
+    # rollout is on the near list and runs the full contact solver) -- the state the planner lives in during pick --, timed
+    # the same way, so that the headline (arm at its initial pose: all rollouts contact-free) is not read on its own
+    contact_rich = None
+    if world == 1 and args.config is None and name == "c4":
+        try:
+            pg, _, _, _ = build_planner(CONFIGS["c4_grasp"], 1, 0, local_rank, "none")
+            pg.set_stream(stream.cuda_stream)
+            for _ in range(3):
+                pg.command_resident()
+            torch.cuda.synchronize()
+            n_g = min(args.steps, 20)
+            evg = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_g)]
+            for i in range(n_g):
+                if flush is not None:
+                    flush.fill_(i & 1)
+                evg[i][0].record(stream)
+                pg.command_resident()
+                evg[i][1].record(stream)
+            torch.cuda.synchronize()
+            msg = float(np.mean([a.elapsed_time(b) for a, b in evg]))
+            ig = pg.command_resident(sync=True)
+            contact_rich = {"name": "c4_grasp", "workload": CONFIGS["c4_grasp"]["workload"], "ms_per_step": msg,
+                            "value": K * T / (msg * 1e-3), "steps": n_g, "near_samples": int(ig.near_samples),
+                            "note": "same K, H and timing as the headline; not part of `value`"}
+            pg.close()
+        except Exception as exc:   # never let the extra leg take the headline line down
+            contact_rich = {"error": repr(exc)}
     clocks = sampler.summary(t_timed0, t_timed1)
     nf = 22 if env == "point_env" else 53
     nu = 2 if env == "point_env" else 9
@@ -511,6 +539,8 @@ def main():
                                          "table or the shelf are rolled out by k_rollout_far (joints + geometry tests + cost only; exact: "
                                          "the full path would skip the same work step by step); the others by the full rollout kernel "
                                          "from their hand-over boundary. bench.py --config c4_grasp is the all-near case"}
+        if contact_rich is not None:
+            line["contact_rich_state"] = contact_rich
         if n1_default is not None:
             line["n1_default_workload_at_this_n"] = n1_default
         if n1_same is not None:
